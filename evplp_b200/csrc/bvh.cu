@@ -1,0 +1,373 @@
+// bvh.cu -- Morton-code LBVH build on the device (replaces the OptiX "Trbvh" acceleration,
+// reference rtcomphoton.h:705-707, and the bounds program meshBound, triangleintersect.cu:62-82).
+//
+// Pipeline (all on the context stream):
+//   1 prim_bounds   per-triangle AABB + scene AABB (ordered-uint atomics)
+//   2 morton        63-bit codes (21 bits/axis) of the box centre
+//   3 CUB radix sort of (code, primId)         -- stable: equal codes keep primitive order
+//   4 leaf_records  triangles rewritten in sorted order with e0/e1/n precomputed
+//   5 karras        Karras 2012 binary radix tree, one thread per internal node
+//   6 refit         bottom-up AABBs (second arriver at a node computes it)
+//   7 collapse      binary tree -> BVH_WIDTH-ary nodes, level by level, surface-area guided
+// Morton codes, sorted order and the binary topology are bit-identical to the CPU twin in
+// the test oracle; the wide nodes are a product-only acceleration (hits do not depend on them).
+#include <cub/device/device_radix_sort.cuh>
+#include "context.h"
+
+namespace evplp {
+
+__device__ __forceinline__ uint32_t enc_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float dec_ordered(uint32_t u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+__global__ void prim_bounds_kernel(const float4* __restrict__ triVerts, int n, float* __restrict__ primLo,
+                                   float* __restrict__ primHi, uint32_t* __restrict__ sceneEnc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (i < n) {
+        float4 a = triVerts[3 * (size_t)i], b = triVerts[3 * (size_t)i + 1], c = triVerts[3 * (size_t)i + 2];
+        lo[0] = fminf(fminf(a.x, b.x), c.x); hi[0] = fmaxf(fmaxf(a.x, b.x), c.x);
+        lo[1] = fminf(fminf(a.y, b.y), c.y); hi[1] = fmaxf(fmaxf(a.y, b.y), c.y);
+        lo[2] = fminf(fminf(a.z, b.z), c.z); hi[2] = fmaxf(fmaxf(a.z, b.z), c.z);
+        for (int k = 0; k < 3; k++) { primLo[3 * (size_t)i + k] = lo[k]; primHi[3 * (size_t)i + k] = hi[k]; }
+    }
+    // warp reduce, then one atomic per warp
+    for (int k = 0; k < 3; k++) {
+        float l = lo[k], h = hi[k];
+        for (int o = 16; o > 0; o >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (l != INFINITY) atomicMin(&sceneEnc[k], enc_ordered(l));
+            if (h != -INFINITY) atomicMax(&sceneEnc[3 + k], enc_ordered(h));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+
+struct Bounds3 {
+    float lo[3], hi[3];
+};
+
+__global__ void morton_kernel(const float* __restrict__ primLo, const float* __restrict__ primHi, int n, Bounds3 scene,
+                              uint64_t* __restrict__ codes, uint32_t* __restrict__ ids) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t g[3];
+    for (int a = 0; a < 3; a++) {
+        float c = (primLo[3 * (size_t)i + a] + primHi[3 * (size_t)i + a]) * 0.5f;
+        float ext = scene.hi[a] - scene.lo[a];
+        float q = ext > 0.0f ? det_div(c - scene.lo[a], ext) : 0.0f;
+        g[a] = (uint32_t)fminf(fmaxf(q * 2097152.0f, 0.0f), 2097151.0f);
+    }
+    codes[i] = (expand21(g[0]) << 2) | (expand21(g[1]) << 1) | expand21(g[2]);
+    ids[i] = (uint32_t)i;
+}
+
+__global__ void leaf_records_kernel(const float4* __restrict__ triVerts, const uint32_t* __restrict__ sorted, int n,
+                                    float4* __restrict__ triLeaf) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t p = sorted[k];
+    float4 a = triVerts[3 * (size_t)p], b = triVerts[3 * (size_t)p + 1], c = triVerts[3 * (size_t)p + 2];
+    V3 p0 = v3(a.x, a.y, a.z), p1 = v3(b.x, b.y, b.z), p2 = v3(c.x, c.y, c.z);
+    V3 e0 = p1 - p0, e1 = p0 - p2;
+    V3 nn = cross(e1, e0);
+    triLeaf[4 * (size_t)k + 0] = make_float4(p0.x, p0.y, p0.z, __int_as_float((int)p));
+    triLeaf[4 * (size_t)k + 1] = make_float4(e0.x, e0.y, e0.z, a.w);  // a.w carries the material index bits
+    triLeaf[4 * (size_t)k + 2] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    triLeaf[4 * (size_t)k + 3] = make_float4(nn.x, nn.y, nn.z, 0.f);
+}
+
+__device__ __forceinline__ int lbvh_delta(const uint64_t* __restrict__ sc, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = sc[i], b = sc[j];
+    if (a == b) return 64 + __clz((int)((uint32_t)i ^ (uint32_t)j));
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void karras_kernel(const uint64_t* __restrict__ sc, int n, int32_t* __restrict__ left,
+                              int32_t* __restrict__ right, int32_t* __restrict__ parent,
+                              int32_t* __restrict__ leafParent, int32_t* __restrict__ rangeFirst,
+                              int32_t* __restrict__ rangeLast) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (lbvh_delta(sc, n, i, i + 1) - lbvh_delta(sc, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = lbvh_delta(sc, n, i, i - d);
+    long long lmax = 2;
+    while (true) {
+        long long j = (long long)i + lmax * d;
+        if (j < 0 || j >= n) break;
+        if (!(lbvh_delta(sc, n, i, (int)j) > dmin)) break;
+        lmax *= 2;
+    }
+    long long l = 0;
+    for (long long t = lmax / 2; t >= 1; t /= 2) {
+        long long j = (long long)i + (l + t) * d;
+        if (j >= 0 && j < n && lbvh_delta(sc, n, i, (int)j) > dmin) l += t;
+    }
+    int j = i + (int)l * d;
+    int dnode = lbvh_delta(sc, n, i, j);
+    long long s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        long long q = (long long)i + (s + t) * d;
+        if (q >= 0 && q < n && lbvh_delta(sc, n, i, (int)q) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + (int)s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    rangeFirst[i] = lo;
+    rangeLast[i] = hi;
+    int L = (lo == gamma) ? ~gamma : gamma;
+    int R = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+    left[i] = L;
+    right[i] = R;
+    if (L >= 0) parent[L] = i; else leafParent[~L] = i;
+    if (R >= 0) parent[R] = i; else leafParent[~R] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__device__ __forceinline__ void child_bounds(int c, const float* __restrict__ nodeBounds, const float* __restrict__ primLo,
+                                             const float* __restrict__ primHi, const uint32_t* __restrict__ sorted, float* b) {
+    if (c >= 0) {
+        for (int k = 0; k < 6; k++) b[k] = nodeBounds[6 * (size_t)c + k];
+    } else {
+        uint32_t p = sorted[~c];
+        for (int k = 0; k < 3; k++) { b[k] = primLo[3 * (size_t)p + k]; b[3 + k] = primHi[3 * (size_t)p + k]; }
+    }
+}
+
+__global__ void refit_kernel(int n, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                             const int32_t* __restrict__ parent, const int32_t* __restrict__ leafParent,
+                             const float* __restrict__ primLo, const float* __restrict__ primHi,
+                             const uint32_t* __restrict__ sorted, float* nodeBounds, uint32_t* flags) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int node = leafParent[k];
+    while (node >= 0) {
+        if (atomicAdd(&flags[node], 1u) == 0u) return;  // first arriver stops; the second sees both children
+        __threadfence();
+        float a[6], b[6];
+        // children's bounds were written (st.cg) before their writer's fence + atomic: read them from L2
+        const int ch[2] = {left[node], right[node]};
+        for (int s = 0; s < 2; s++) {
+            float* dst = s ? b : a;
+            if (ch[s] >= 0) {
+                for (int q = 0; q < 6; q++) dst[q] = __ldcg(&nodeBounds[6 * (size_t)ch[s] + q]);
+            } else {
+                uint32_t p = sorted[~ch[s]];
+                for (int q = 0; q < 3; q++) { dst[q] = primLo[3 * (size_t)p + q]; dst[3 + q] = primHi[3 * (size_t)p + q]; }
+            }
+        }
+        for (int q = 0; q < 3; q++) {
+            __stcg(&nodeBounds[6 * (size_t)node + q], fminf(a[q], b[q]));
+            __stcg(&nodeBounds[6 * (size_t)node + 3 + q], fmaxf(a[3 + q], b[3 + q]));
+        }
+        __threadfence();
+        node = parent[node];
+    }
+}
+
+__device__ __forceinline__ float half_area(const float* b) {
+    float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// One level of the wide collapse.  Work item = (binary internal node, wide node slot).
+__global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ counters, int level,
+                                uint32_t* __restrict__ queueOut, uint32_t* countersOut,
+                                const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                const int32_t* __restrict__ rangeFirst, const int32_t* __restrict__ rangeLast,
+                                const float* __restrict__ nodeBounds, const float* __restrict__ primLo,
+                                const float* __restrict__ primHi, const uint32_t* __restrict__ sorted, float pad,
+                                WideNode* __restrict__ nodes) {
+    // counters: [0] = number of wide nodes allocated, [1 + (level&1)] = items in queueIn, [1 + (~level&1)] = out count
+    const uint32_t numIn = counters[1 + (level & 1)];
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= numIn) return;
+    const int bin = (int)queueIn[2 * (size_t)w];
+    const uint32_t slot = queueIn[2 * (size_t)w + 1];
+    int cand[BVH_WIDTH];
+    int nc = 2;
+    cand[0] = left[bin];
+    cand[1] = right[bin];
+    while (nc < BVH_WIDTH) {
+        int best = -1;
+        float bestArea = -1.f;
+        for (int k = 0; k < nc; k++) {
+            int c = cand[k];
+            if (c < 0) continue;
+            if (rangeLast[c] - rangeFirst[c] + 1 <= BVH_LEAF_MAX) continue;
+            float a = half_area(nodeBounds + 6 * (size_t)c);
+            if (a > bestArea) { bestArea = a; best = k; }
+        }
+        if (best < 0) break;
+        int c = cand[best];
+        cand[best] = left[c];
+        cand[nc++] = right[c];
+    }
+    WideNode nd;
+    for (int k = 0; k < BVH_WIDTH; k++) {
+        if (k >= nc) {
+            nd.lox[k] = nd.loy[k] = nd.loz[k] = INFINITY;
+            nd.hix[k] = nd.hiy[k] = nd.hiz[k] = -INFINITY;
+            nd.child[k] = BVH_EMPTY;
+            continue;
+        }
+        int c = cand[k];
+        float b[6];
+        child_bounds(c, nodeBounds, primLo, primHi, sorted, b);
+        nd.lox[k] = b[0] - pad; nd.loy[k] = b[1] - pad; nd.loz[k] = b[2] - pad;
+        nd.hix[k] = b[3] + pad; nd.hiy[k] = b[4] + pad; nd.hiz[k] = b[5] + pad;
+        if (c < 0) {
+            nd.child[k] = bvh_make_leaf((uint32_t)(~c), 1u);
+        } else {
+            int cnt = rangeLast[c] - rangeFirst[c] + 1;
+            if (cnt <= BVH_LEAF_MAX) {
+                nd.child[k] = bvh_make_leaf((uint32_t)rangeFirst[c], (uint32_t)cnt);
+            } else {
+                uint32_t idx = atomicAdd(&countersOut[0], 1u);
+                uint32_t q = atomicAdd(&countersOut[1 + ((level + 1) & 1)], 1u);
+                queueOut[2 * (size_t)q] = (uint32_t)c;
+                queueOut[2 * (size_t)q + 1] = idx;
+                nd.child[k] = idx;
+            }
+        }
+    }
+    nodes[slot] = nd;
+}
+
+// Scene with <= BVH_LEAF_MAX triangles: one node, one leaf child.
+__global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const float* __restrict__ primHi, float pad,
+                                 WideNode* nodes) {
+    WideNode nd;
+    float b[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) { b[k] = fminf(b[k], primLo[3 * i + k]); b[3 + k] = fmaxf(b[3 + k], primHi[3 * i + k]); }
+    for (int k = 0; k < BVH_WIDTH; k++) {
+        nd.lox[k] = nd.loy[k] = nd.loz[k] = INFINITY;
+        nd.hix[k] = nd.hiy[k] = nd.hiz[k] = -INFINITY;
+        nd.child[k] = BVH_EMPTY;
+    }
+    nd.lox[0] = b[0] - pad; nd.loy[0] = b[1] - pad; nd.loz[0] = b[2] - pad;
+    nd.hix[0] = b[3] + pad; nd.hiy[0] = b[4] + pad; nd.hiz[0] = b[5] + pad;
+    nd.child[0] = bvh_make_leaf(0u, (uint32_t)n);
+    nodes[0] = nd;
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (err) *err = std::string(#x) + ": " + cudaGetErrorString(e_); return e_; } } while (0)
+
+cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
+    const int n = c->numPrims;
+    cudaStream_t st = c->stream;
+    c->numNodes = 0;
+    c->bvhBuilt = false;
+    if (n == 0) { c->bvhBuilt = true; return cudaSuccess; }
+    const int nInt = n > 1 ? n - 1 : 0;
+    CK(c->primLo.reserve(3 * (size_t)n)); CK(c->primHi.reserve(3 * (size_t)n));
+    CK(c->codes.reserve(n)); CK(c->codesSorted.reserve(n));
+    CK(c->primIds.reserve(n)); CK(c->primIdsSorted.reserve(n));
+    CK(c->triLeaf.reserve(4 * (size_t)n));
+    CK(c->left.reserve(nInt)); CK(c->right.reserve(nInt)); CK(c->parent.reserve(nInt));
+    CK(c->leafParent.reserve(n)); CK(c->rangeFirst.reserve(nInt)); CK(c->rangeLast.reserve(nInt));
+    CK(c->nodeBounds.reserve(6 * (size_t)nInt)); CK(c->refitFlags.reserve(nInt));
+    CK(c->nodes.reserve(nInt > 0 ? nInt : 1));
+    CK(c->sceneBoundsEnc.reserve(6));
+    CK(c->queueA.reserve(2 * (size_t)(nInt + 1))); CK(c->queueB.reserve(2 * (size_t)(nInt + 1)));
+    CK(c->counters.reserve(4));
+
+    const int TB = 256;
+    const int gridN = (n + TB - 1) / TB;
+    // 1 bounds
+    uint32_t encInit[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(c->sceneBoundsEnc.p, encInit, sizeof(encInit), cudaMemcpyHostToDevice, st));
+    prim_bounds_kernel<<<gridN, TB, 0, st>>>(c->triVerts.p, n, c->primLo.p, c->primHi.p, c->sceneBoundsEnc.p);
+    c->launches++;
+    uint32_t enc[6];
+    CK(cudaMemcpyAsync(enc, c->sceneBoundsEnc.p, sizeof(enc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    Bounds3 sb;
+    float m = 0.f;
+    for (int k = 0; k < 3; k++) {
+        sb.lo[k] = dec_ordered(enc[k]); sb.hi[k] = dec_ordered(enc[3 + k]);
+        c->sceneMin[k] = sb.lo[k]; c->sceneMax[k] = sb.hi[k];
+        m = fmaxf(m, fmaxf(fabsf(sb.lo[k]), fabsf(sb.hi[k])));
+    }
+    c->boxPad = m * 1e-5f + 1e-20f;
+    // 2 codes
+    morton_kernel<<<gridN, TB, 0, st>>>(c->primLo.p, c->primHi.p, n, sb, c->codes.p, c->primIds.p);
+    c->launches++;
+    // 3 sort (stable LSD radix sort over the 63 used bits)
+    size_t tempBytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, c->codes.p, c->codesSorted.p, c->primIds.p, c->primIdsSorted.p, n, 0, 63, st));
+    CK(c->sortTemp.reserve(tempBytes));
+    CK(cub::DeviceRadixSort::SortPairs(c->sortTemp.p, tempBytes, c->codes.p, c->codesSorted.p, c->primIds.p, c->primIdsSorted.p, n, 0, 63, st));
+    c->launches += 9;  // histogram + onesweep passes (CUB-internal; counted approximately)
+    // 4 leaf records
+    leaf_records_kernel<<<gridN, TB, 0, st>>>(c->triVerts.p, c->primIdsSorted.p, n, c->triLeaf.p);
+    c->launches++;
+    if (n <= BVH_LEAF_MAX) {
+        tiny_root_kernel<<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->nodes.p);
+        c->launches++;
+        CK(cudaStreamSynchronize(st));
+        c->numNodes = 1;
+        c->bvhBuilt = true;
+        return cudaSuccess;
+    }
+    // 5 topology
+    const int gridI = (nInt + TB - 1) / TB;
+    karras_kernel<<<gridI, TB, 0, st>>>(c->codesSorted.p, n, c->left.p, c->right.p, c->parent.p, c->leafParent.p,
+                                        c->rangeFirst.p, c->rangeLast.p);
+    c->launches++;
+    // 6 refit
+    CK(cudaMemsetAsync(c->refitFlags.p, 0, sizeof(uint32_t) * nInt, st));
+    refit_kernel<<<gridN, TB, 0, st>>>(n, c->left.p, c->right.p, c->parent.p, c->leafParent.p, c->primLo.p, c->primHi.p,
+                                       c->primIdsSorted.p, c->nodeBounds.p, c->refitFlags.p);
+    c->launches++;
+    // 7 collapse
+    uint32_t init[4] = {1u, 1u, 0u, 0u};  // one wide node (root), one item in queue A
+    uint32_t rootItem[2] = {0u, 0u};
+    CK(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->queueA.p, rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, st));
+    uint32_t numIn = 1;
+    int level = 0;
+    while (numIn > 0) {
+        uint32_t* qin = (level & 1) ? c->queueB.p : c->queueA.p;
+        uint32_t* qout = (level & 1) ? c->queueA.p : c->queueB.p;
+        CK(cudaMemsetAsync(c->counters.p + 1 + ((level + 1) & 1), 0, sizeof(uint32_t), st));
+        collapse_kernel<<<(numIn + 127) / 128, 128, 0, st>>>(qin, c->counters.p, level, qout, c->counters.p, c->left.p,
+                                                            c->right.p, c->rangeFirst.p, c->rangeLast.p, c->nodeBounds.p,
+                                                            c->primLo.p, c->primHi.p, c->primIdsSorted.p, c->boxPad,
+                                                            c->nodes.p);
+        c->launches++;
+        uint32_t cnt[3];
+        CK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        numIn = cnt[1 + ((level + 1) & 1)];
+        c->numNodes = (int)cnt[0];
+        level++;
+        if (level > 4096) { if (err) *err = "wide collapse did not terminate"; return cudaErrorUnknown; }
+    }
+    CK(cudaGetLastError());
+    c->bvhBuilt = true;
+    return cudaSuccess;
+}
+
+}  // namespace evplp

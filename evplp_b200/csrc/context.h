@@ -1,0 +1,120 @@
+// context.h -- the opaque EvplpContext behind evplp_handle (one per GPU) and the
+// internal launch interface between the C ABI (capi.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/evplp.h"
+#include "device_scene.h"
+
+namespace evplp {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;  // capacity in elements
+    cudaError_t reserve(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+enum Stage { ST_BVH = 0, ST_GBUFFER, ST_LIGHT_TRACE, ST_GATHER, ST_SPLAT, ST_RESOLVE, ST_COUNT };
+
+struct DevStats {
+    unsigned long long shadowRays, splatPhotons, splatFragments, closestRays, gatherPairs;
+    int stackOverflow;
+    int pad;
+};
+
+}  // namespace evplp
+
+struct EvplpContext {
+    int device = 0;
+    int W = 0, H = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    float stageMs[evplp::ST_COUNT] = {0, 0, 0, 0, 0, 0};
+    uint64_t launches = 0;
+
+    // scene
+    evplp::DevBuf<float4> triVerts, triLeaf, texPool;
+    evplp::DevBuf<float2> triUV;
+    evplp::DevBuf<evplp::DevMaterial> mats;
+    evplp::DevBuf<float> lightCdf;
+    int numPrims = 0, numMats = 0;
+    int lightFirst = 0, lightCount = 0;
+    float lightArea = 0.f;
+    float lightIntensity[4] = {0, 0, 0, 0}, lightDisplay[4] = {0, 0, 0, 0};
+    bool sceneLoaded = false;
+
+    // BVH
+    evplp::DevBuf<float> primLo, primHi;          // 3 floats per primitive, original order
+    evplp::DevBuf<uint64_t> codes, codesSorted;
+    evplp::DevBuf<uint32_t> primIds, primIdsSorted;
+    evplp::DevBuf<int32_t> left, right, parent, leafParent, rangeFirst, rangeLast;
+    evplp::DevBuf<float> nodeBounds;              // 6 floats per binary internal node
+    evplp::DevBuf<uint32_t> refitFlags;
+    evplp::DevBuf<evplp::WideNode> nodes;
+    evplp::DevBuf<uint32_t> sceneBoundsEnc;       // 6 ordered-uint encodings
+    evplp::DevBuf<uint8_t> sortTemp;
+    evplp::DevBuf<uint32_t> queueA, queueB, counters;
+    float sceneMin[3] = {0, 0, 0}, sceneMax[3] = {0, 0, 0};
+    float boxPad = 0.f;
+    int numNodes = 0;
+    bool bvhBuilt = false;
+
+    // per-iteration state
+    EvplpParams params;
+    bool paramsSet = false;
+    evplp::DevBuf<uint32_t> skipMatrix;           // 800 words: composed XORWOW skip matrix
+    uint32_t skipMatrixSeed = 0xffffffffu;
+    bool skipMatrixValid = false;
+
+    evplp::DevBuf<EvplpRecord> records;
+    uint64_t numRecords = 0;                      // valid records of the last trace / upload
+    uint32_t recordsFirstPath = 0;
+    evplp::DevBuf<uint32_t> vplList;              // indices of usable VPL records (gather prefix)
+    evplp::DevBuf<uint32_t> photonList;           // indices of usable photon records
+
+    evplp::DevBuf<float4> gbuf;                   // 4 planes of W*H
+    evplp::DevBuf<int32_t> gprim;
+    bool gbufValid = false;
+
+    evplp::DevBuf<long long> accVpl, accPhoton;   // Q31.32, W*H*3
+    evplp::DevBuf<uint32_t> accLight;             // W*H
+    evplp::DevBuf<float> resolveOut;              // W*H*3
+    float* resolvePinned = nullptr;
+
+    evplp::DevBuf<evplp::DevStats> devStats;
+    EvplpStats stats;
+
+    evplp::DevScene scene() const;
+};
+
+namespace evplp {
+
+// bvh.cu
+cudaError_t build_bvh_device(EvplpContext* c, std::string* err);
+// stages.cu
+cudaError_t launch_gbuffer(EvplpContext* c);
+cudaError_t launch_light_trace(EvplpContext* c, uint32_t rngSeed, uint32_t firstPath, uint32_t numPaths);
+cudaError_t launch_gather(EvplpContext* c, EvplpTile tile, int mode);
+cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numRecords, EvplpTile tile);
+cudaError_t launch_light_pass(EvplpContext* c);
+cudaError_t launch_resolve(EvplpContext* c, float vplScale, float photonScale, float lightScale, int gamma);
+cudaError_t launch_trace_rays(EvplpContext* c, const float* devRays, uint64_t n, int anyHit, int32_t* devPrim, float* devT);
+cudaError_t launch_debug_uniforms(EvplpContext* c, uint32_t seed, uint32_t n, float* devOut);
+cudaError_t launch_debug_curand(EvplpContext* c, uint32_t seed, uint32_t subsequence, uint32_t n, float* devOut);
+cudaError_t launch_debug_math(EvplpContext* c, int op, const float* x, const float* y, uint32_t n, float* out);
+// host_xorwow.cpp
+void xorwow_compose_skip(uint32_t subsequence, uint32_t* out800);
+
+}  // namespace evplp

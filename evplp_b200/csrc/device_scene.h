@@ -1,0 +1,246 @@
+// device_scene.h -- HBM layout of the scene and the wide BVH, plus the traversal routines
+// that replace rtTrace / meshFineIntersect / rtMaterialAnyHit
+// (reference: triangleintersect.cu:17-41, lighttracing.cu:184-188,236,292; the OptiX
+// "Trbvh" acceleration set up at rtcomphoton.h:705-707).
+//
+// Layout
+//   triLeaf[4*k .. 4*k+3]  one triangle in BVH-leaf (Morton) order, 64 B:
+//        {p0.xyz, primId} {e0.xyz, matIndex} {e1.xyz, -} {n.xyz, -}
+//        e0 = p1-p0, e1 = p0-p2, n = cross(e1,e0): the ray-independent part of
+//        optix::intersect_triangle_branchless, precomputed with the same roundings.
+//   triVerts[3*p .. 3*p+2] original primitive order {p0.xyz, mat} {p1.xyz,-} {p2.xyz,-}
+//   triUV[3*p .. 3*p+2]    original order texcoords t0,t1,t2
+//   nodes[]                BVH_WIDTH-ary nodes, SoA child boxes (padded), 128 B aligned
+//
+// Hit semantics (identical to the oracle): a triangle is hit iff the branchless test
+// accepts it; closest hit = smallest t, ties -> smallest primitive id; any hit = exists.
+// Box tests are only a conservative cull: boxes are padded by 1e-5 * scene scale.
+#pragma once
+#include <cuda_runtime.h>
+#include "shading.h"
+
+namespace evplp {
+
+constexpr int BVH_WIDTH = 4;
+constexpr int BVH_LEAF_MAX = 4;             // triangles per leaf child
+constexpr uint32_t BVH_EMPTY = 0x7fffffffu;
+constexpr uint32_t BVH_LEAF_BIT = 0x80000000u;
+constexpr int BVH_STACK = 96;
+
+struct alignas(128) WideNode {
+    float lox[BVH_WIDTH], loy[BVH_WIDTH], loz[BVH_WIDTH];
+    float hix[BVH_WIDTH], hiy[BVH_WIDTH], hiz[BVH_WIDTH];
+    uint32_t child[BVH_WIDTH];  // EMPTY | LEAF_BIT | (count-1) << 27 | first   or   node index
+};
+
+EVPLP_HD uint32_t bvh_make_leaf(uint32_t first, uint32_t count) { return BVH_LEAF_BIT | ((count - 1u) << 27) | first; }
+EVPLP_HD uint32_t bvh_leaf_first(uint32_t c) { return c & 0x07ffffffu; }
+EVPLP_HD uint32_t bvh_leaf_count(uint32_t c) { return ((c >> 27) & 0xfu) + 1u; }
+
+struct DevScene {
+    const float4* triLeaf;
+    const float4* triVerts;
+    const float2* triUV;
+    const DevMaterial* mats;
+    const float4* texPool;
+    const float* lightCdf;
+    const WideNode* nodes;
+    int numPrims;
+    int numNodes;
+    int lightFirst, lightCount;
+    float lightArea;
+    float lightIntensity[4];  // pi-scaled rgb, .w = emission exponent
+    float lightDisplay[4];
+};
+
+struct RayHit {
+    int prim;
+    float t, beta, gamma;
+    V3 n;  // un-normalised cross(e1, e0)
+    int mat;
+};
+
+#if defined(__CUDACC__)
+
+// Per-ray constants of the slab test: t = lo * inv - org*inv (one FMA per plane).
+struct RaySlab {
+    float ix, iy, iz, ox, oy, oz;
+};
+__device__ __forceinline__ RaySlab make_slab(V3 org, V3 dir) {
+    RaySlab s;
+    // a zero component would give inf * 0 = NaN products; a tiny one keeps the test finite
+    float dx = fabsf(dir.x) < 1e-30f ? copysignf(1e-30f, dir.x) : dir.x;
+    float dy = fabsf(dir.y) < 1e-30f ? copysignf(1e-30f, dir.y) : dir.y;
+    float dz = fabsf(dir.z) < 1e-30f ? copysignf(1e-30f, dir.z) : dir.z;
+    s.ix = __frcp_rn(dx); s.iy = __frcp_rn(dy); s.iz = __frcp_rn(dz);
+    s.ox = org.x * s.ix; s.oy = org.y * s.iy; s.oz = org.z * s.iz;
+    return s;
+}
+
+// entry distance of child c (clipped to [tmin, tmax]); returns whether the slab interval is non-empty
+__device__ __forceinline__ bool slab_test(const RaySlab& s, const WideNode& nd, int c, float tmin, float tmax, float* tnear) {
+    float x0 = __fmaf_rn(nd.lox[c], s.ix, -s.ox), x1 = __fmaf_rn(nd.hix[c], s.ix, -s.ox);
+    float y0 = __fmaf_rn(nd.loy[c], s.iy, -s.oy), y1 = __fmaf_rn(nd.hiy[c], s.iy, -s.oy);
+    float z0 = __fmaf_rn(nd.loz[c], s.iz, -s.oz), z1 = __fmaf_rn(nd.hiz[c], s.iz, -s.oz);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    *tnear = tn;
+    return tn <= tf;
+}
+
+// optix::intersect_triangle_branchless with the ray-independent terms precomputed.
+__device__ __forceinline__ bool tri_test(V3 org, V3 dir, float tmin, float tmax, V3 p0, V3 e0, V3 e1, V3 n,
+                                         float* t, float* beta, float* gamma) {
+    const float inv = det_div(1.0f, dot(n, dir));
+    const V3 e2 = inv * (p0 - org);
+    const V3 i = cross(dir, e2);
+    *beta = dot(i, e1);
+    *gamma = dot(i, e0);
+    *t = dot(n, e2);
+    return (*t < tmax) & (*t > tmin) & (*beta >= 0.0f) & (*gamma >= 0.0f) & (*beta + *gamma <= 1.0f);
+}
+
+__device__ __forceinline__ V3 ld3(const float4& v) { return v3(v.x, v.y, v.z); }
+
+// Closest hit, one ray per thread, private stack.
+__device__ inline RayHit trace_closest(const DevScene& sc, V3 org, V3 dir, float tmin, float tmax, int* overflow) {
+    RayHit best;
+    best.prim = -1; best.t = 0.f; best.beta = 0.f; best.gamma = 0.f; best.n = v3s(0.f); best.mat = 0;
+    if (sc.numNodes == 0) return best;
+    float bestT = tmax;
+    const RaySlab slab = make_slab(org, dir);
+    uint32_t stack[BVH_STACK];
+    int sp = 0;
+    uint32_t cur = 0;  // root node
+    while (true) {
+        if (cur & BVH_LEAF_BIT) {
+            const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
+            for (uint32_t k = 0; k < count; k++) {
+                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+                float t, be, ga;
+                if (tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) {
+                    const int prim = __float_as_int(a.w);
+                    if (best.prim < 0 ? (t < bestT) : (t < bestT || (t == bestT && prim < best.prim))) {
+                        best.prim = prim; best.t = t; best.beta = be; best.gamma = ga; best.n = ld3(d);
+                        best.mat = __float_as_int(b.w);
+                        bestT = t;
+                    }
+                }
+            }
+        } else {
+            const WideNode& nd = sc.nodes[cur];
+            float tn[BVH_WIDTH];
+            uint32_t ch[BVH_WIDTH];
+            int nh = 0;
+#pragma unroll
+            for (int c = 0; c < BVH_WIDTH; c++) {
+                float t;
+                const uint32_t cd = nd.child[c];
+                if (cd != BVH_EMPTY && slab_test(slab, nd, c, tmin, bestT, &t)) {
+                    // insertion sort by entry distance, nearest last (popped first)
+                    int j = nh++;
+                    while (j > 0 && tn[j - 1] < t) { tn[j] = tn[j - 1]; ch[j] = ch[j - 1]; j--; }
+                    tn[j] = t; ch[j] = cd;
+                }
+            }
+            for (int j = 0; j < nh; j++) {
+                if (sp < BVH_STACK) stack[sp++] = ch[j]; else *overflow = 1;
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return best;
+}
+
+// Any hit, one ray per thread, private stack.
+__device__ inline bool trace_any(const DevScene& sc, V3 org, V3 dir, float tmin, float tmax, int* overflow) {
+    if (sc.numNodes == 0) return false;
+    const RaySlab slab = make_slab(org, dir);
+    uint32_t stack[BVH_STACK];
+    int sp = 0;
+    uint32_t cur = 0;
+    while (true) {
+        if (cur & BVH_LEAF_BIT) {
+            const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
+            for (uint32_t k = 0; k < count; k++) {
+                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+                float t, be, ga;
+                if (tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) return true;
+            }
+        } else {
+            const WideNode& nd = sc.nodes[cur];
+#pragma unroll
+            for (int c = 0; c < BVH_WIDTH; c++) {
+                float t;
+                const uint32_t cd = nd.child[c];
+                if (cd != BVH_EMPTY && slab_test(slab, nd, c, tmin, tmax, &t)) {
+                    if (sp < BVH_STACK) stack[sp++] = cd; else *overflow = 1;
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return false;
+}
+
+// Any hit for a whole warp at once: the 32 rays walk the tree together with ONE shared
+// stack (in shared memory), so every node / triangle is fetched once per warp (uniform
+// address -> broadcast) and there is no divergence.  Rays of the gather are coherent
+// (neighbouring pixels, same VPL), so the union of their paths is barely larger than one
+// ray's.  `active` lanes carry a ray; returns per lane whether it is occluded.
+// Must be called by all 32 lanes.
+__device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V3 dir, float tmin, float tmax,
+                                      uint32_t* warpStack /* BVH_STACK entries in smem */, int* overflow) {
+    const unsigned full = 0xffffffffu;
+    bool open = active;  // still needs an answer
+    bool occluded = false;
+    if (sc.numNodes == 0 || !__any_sync(full, open)) return false;
+    const RaySlab slab = make_slab(org, dir);
+    const int lane = threadIdx.x & 31;
+    int sp = 0;
+    uint32_t cur = 0;
+    while (true) {
+        if (cur & BVH_LEAF_BIT) {
+            const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
+            for (uint32_t k = 0; k < count; k++) {
+                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+                float t, be, ga;
+                if (open && tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) {
+                    occluded = true;
+                    open = false;
+                }
+            }
+            if (!__any_sync(full, open)) break;
+        } else {
+            const WideNode& nd = sc.nodes[cur];
+            uint32_t push[BVH_WIDTH];
+            int np = 0;
+#pragma unroll
+            for (int c = 0; c < BVH_WIDTH; c++) {
+                float t;
+                const uint32_t cd = nd.child[c];
+                bool want = open && cd != BVH_EMPTY && slab_test(slab, nd, c, tmin, tmax, &t);
+                if (__any_sync(full, want)) push[np++] = cd;
+            }
+            if (sp + np > BVH_STACK) { *overflow = 1; np = BVH_STACK - sp; }
+            if (lane == 0) {
+                for (int j = 0; j < np; j++) warpStack[sp + j] = push[j];
+            }
+            sp += np;
+            __syncwarp();
+        }
+        if (sp == 0) break;
+        cur = warpStack[--sp];
+        __syncwarp();
+    }
+    return occluded;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace evplp

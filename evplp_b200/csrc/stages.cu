@@ -1,0 +1,886 @@
+// stages.cu -- the per-iteration kernels of the EVPLP hot path (sm_100a).
+//
+//   gbuffer_kernel       replaces runDeferredProgram + deferred.{vert,geom,frag}   (rtcomphoton.h:710-754)
+//   light_trace_kernel   replaces tracePhotons + rtMaterialClosestHit              (lighttracing.cu:113-250)
+//   gather_vpl_kernel    replaces splatColor + vplSplat + rtMaterialAnyHit         (lighttracing.cu:184-188,275-379)
+//   gather_vsl_kernel    replaces splatSplotch + vslSplat + sample*                (lighttracing.cu:382-722)
+//   gather_lvc_kernel    replaces the LVC splatColor                               (lvclighttracing.cu:348-387)
+//   splat_kernel         replaces runPhotonSplat + photonsplatinstanced.*          (rtcomphoton.h:789-837)
+//   light_pass_kernel    replaces runLightProgram + light.frag                     (rtcomphoton.h:839-855)
+//   resolve_kernel       replaces runFinalProgram + final.frag                     (rtcomphoton.h:756-787)
+//
+// Compiled with -fmad=false: all shading arithmetic rounds exactly as written (shading.h).
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <curand_kernel.h>
+#include "context.h"
+
+namespace evplp {
+
+// ------------------------------------------------------------------ helpers -------------
+__device__ __forceinline__ Vertex load_vertex(const float4* r) {
+    Vertex v;
+    float4 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5];
+    v.pos = v3(a.x, a.y, a.z);
+    v.normal = v3(b.x, b.y, b.z); v.pSel = b.w;
+    v.flux = v3(c.x, c.y, c.z);
+    v.fluxDir = v3(d.x, d.y, d.z);
+    v.kd = v3(e.x, e.y, e.z);
+    v.ks = v3(f.x, f.y, f.z); v.exponent = f.w;
+    return v;
+}
+
+__device__ __forceinline__ void store_record(EvplpRecord* rec, V3 pos, uint32_t flags, V3 n, float pSel, V3 flux, V3 fluxDir,
+                                             V3 kd, V3 ks, float e) {
+    float4* r = reinterpret_cast<float4*>(rec);
+    r[0] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(flags));
+    r[1] = make_float4(n.x, n.y, n.z, pSel);
+    r[2] = make_float4(flux.x, flux.y, flux.z, 0.f);
+    r[3] = make_float4(fluxDir.x, fluxDir.y, fluxDir.z, 0.f);
+    r[4] = make_float4(kd.x, kd.y, kd.z, 0.f);
+    r[5] = make_float4(ks.x, ks.y, ks.z, e);
+}
+
+__device__ __forceinline__ void zero_record(EvplpRecord* rec) {
+    float4* r = reinterpret_cast<float4*>(rec);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 6; k++) r[k] = z;
+}
+
+__device__ __forceinline__ Surface load_surface(const float4* __restrict__ gbuf, size_t n, size_t i, float* w) {
+    Surface s;
+    float4 a = gbuf[i], b = gbuf[n + i], c = gbuf[2 * n + i], d = gbuf[3 * n + i];
+    s.pos = v3(a.x, a.y, a.z); *w = a.w;
+    s.normal = v3(b.x, b.y, b.z);
+    s.kd = v3(c.x, c.y, c.z);
+    s.ks = v3(d.x, d.y, d.z); s.exponent = d.w;
+    return s;
+}
+
+struct CamParams {
+    V3 pos, fwd, right, up;
+    float tanX, tanY, jx, jy, nearD, farD;
+};
+
+static CamParams cam_of(const EvplpParams& P) {
+    CamParams c;
+    c.pos = v3p(P.cameraPosition); c.fwd = v3p(P.camForward); c.right = v3p(P.camRight); c.up = v3p(P.camUp);
+    c.tanX = P.tanHalfFovX; c.tanY = P.tanHalfFovY; c.jx = P.jitter[0]; c.jy = P.jitter[1];
+    c.nearD = P.nearDist; c.farD = P.farDist;
+    return c;
+}
+
+// ------------------------------------------------------------------ G-buffer ------------
+__global__ void __launch_bounds__(128) gbuffer_kernel(DevScene sc, CamParams cam, int W, int H, float4* __restrict__ gbuf,
+                                                      int32_t* __restrict__ gprim, DevStats* stats) {
+    // 8x4 pixel tiles per warp keep primary rays coherent
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= W || y >= H) return;
+    const size_t n = (size_t)W * H, i = (size_t)y * W + x;
+    float cx = det_div((float)x + 0.5f, (float)W) * 2.0f - 1.0f;
+    float cy = det_div((float)y + 0.5f, (float)H) * 2.0f - 1.0f;
+    float nx = (cx - cam.jx) * cam.tanX;
+    float ny = (cy - cam.jy) * cam.tanY;
+    V3 dir = cam.fwd + cam.right * nx + cam.up * ny;
+    int ovf = 0;
+    RayHit hit = trace_closest(sc, cam.pos, dir, cam.nearD, cam.farD, &ovf);
+    if (ovf) stats->stackOverflow = 1;
+    float4 o0 = make_float4(0.f, 0.f, 0.f, 1.f), o1 = make_float4(0.f, 0.f, 0.f, 0.f), o2 = o1, o3 = o1;
+    if (hit.prim >= 0) {
+        const float4 a = sc.triVerts[3 * (size_t)hit.prim], b = sc.triVerts[3 * (size_t)hit.prim + 1],
+                     c = sc.triVerts[3 * (size_t)hit.prim + 2];
+        const V3 p0 = ld3(a), p1 = ld3(b), p2 = ld3(c);
+        const float w0 = 1.0f - hit.beta - hit.gamma;
+        V3 pos = p0 * w0 + p1 * hit.beta + p2 * hit.gamma;        // deferred.geom:23 (interpolated world position)
+        V3 nrm = normalize(cross(p1 - p0, p2 - p0));              // deferred.geom:16-18 (flat, not face-forwarded)
+        const float2 t0 = sc.triUV[3 * (size_t)hit.prim], t1 = sc.triUV[3 * (size_t)hit.prim + 1],
+                     t2 = sc.triUV[3 * (size_t)hit.prim + 2];
+        float u = t0.x * w0 + t1.x * hit.beta + t2.x * hit.gamma;
+        float v = t0.y * w0 + t1.y * hit.beta + t2.y * hit.gamma;
+        const DevMaterial& m = sc.mats[hit.mat];
+        Texel4 kd = tex_fetch(m.lambert, sc.texPool, u, v);
+        Texel4 ks = tex_fetch(m.phong, sc.texPool, u, v);
+        Texel4 ex = tex_fetch(m.exponent, sc.texPool, u, v);
+        o0 = make_float4(pos.x, pos.y, pos.z, 1.f);
+        o1 = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+        o2 = make_float4(kd.x, kd.y, kd.z, 0.f);
+        o3 = make_float4(ks.x, ks.y, ks.z, ex.x);
+    }
+    gbuf[i] = o0; gbuf[n + i] = o1; gbuf[2 * n + i] = o2; gbuf[3 * n + i] = o3;
+    gprim[i] = hit.prim;
+}
+
+// ------------------------------------------------------------------ light tracing -------
+__global__ void __launch_bounds__(128) light_trace_kernel(DevScene sc, const uint32_t* __restrict__ skip,
+                                                          EvplpRecord* __restrict__ records, uint32_t firstPath,
+                                                          uint32_t numPaths, uint32_t B1, DevStats* stats) {
+    __shared__ uint32_t sm[kSkipMatrixWords];
+    for (int k = threadIdx.x; k < kSkipMatrixWords; k += blockDim.x) sm[k] = skip[k];
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numPaths) return;
+    EvplpRecord* rec = records + (size_t)i * B1;
+
+    // curand_init(launchId, rngSeed, 0) -- lighttracing.cu:203
+    Xorwow rng = xorwow_seed(firstPath + i);
+    xorwow_apply_matrix(rng, sm);
+
+    // LightSample -- rtlightsource.cuh:24-80
+    V3 position, normal, flux;
+    {
+        float randNum = xorwow_uniform(rng);
+        unsigned count = (unsigned)sc.lightCount, first = 0;
+        while (count > 0) {
+            unsigned step = count / 2;
+            unsigned it = first + step;
+            if (sc.lightCdf[it] < randNum) { first = it + 1; count -= step + 1; } else { count = step; }
+        }
+        const size_t prim = (size_t)sc.lightFirst + first;
+        const V3 pos1 = ld3(sc.triVerts[3 * prim]), pos2 = ld3(sc.triVerts[3 * prim + 1]), pos3 = ld3(sc.triVerts[3 * prim + 2]);
+        float bx = xorwow_uniform(rng);
+        float by = xorwow_uniform(rng);
+        float beta, gamma;
+        square_to_barycentric(&beta, &gamma, bx, by);
+        position = pos1 * beta + pos2 * gamma + pos3 * (1.0f - gamma - beta);
+        normal = normalize(cross(pos2 - pos1, pos3 - pos1));
+        flux = v3(sc.lightIntensity[0], sc.lightIntensity[1], sc.lightIntensity[2]) * sc.lightArea;
+    }
+    V3 direction;
+    float pdfW;
+    V3 att = phong_sample(&direction, &pdfW, normal, normal, v3s(1.0f), sc.lightIntensity[3], rng);
+    store_record(rec, position, EVPLP_FLAG_USABLE_VPL, normal, 0.0f, flux, normal, v3s(0.0f), v3s(1.0f), sc.lightIntensity[3]);
+
+    V3 pflux = flux * att;
+    V3 nextPosition = position, nextDirection = direction;
+    uint32_t written = 1;
+    unsigned long long rays = 0;
+    int ovf = 0;
+    for (uint32_t b = 1; b < B1; b++) {
+        const V3 rayOrigin = nextPosition, rayDirection = nextDirection;
+        const uint32_t flag = (b != B1 - 1) ? (EVPLP_FLAG_USABLE_VPL | EVPLP_FLAG_USABLE_PHOTON) : EVPLP_FLAG_USABLE_PHOTON;
+        rays++;
+        RayHit hit = trace_closest(sc, rayOrigin, rayDirection, 0.0001f, 1e27f, &ovf);
+        if (hit.prim < 0) break;  // no miss program: the path ends
+        // rtMaterialClosestHit -- lighttracing.cu:113-182
+        const DevMaterial& mat = sc.mats[hit.mat];
+        V3 geometryNormal = normalize(hit.n);
+        V3 worldGeometryNormal = normalize(geometryNormal);
+        V3 ffNormal = faceforward(worldGeometryNormal, -rayDirection, worldGeometryNormal);
+        V3 hitPosition = rayOrigin + hit.t * rayDirection;
+        if (dot(geometryNormal, rayDirection) > 0.f || mat.lightIntensity[0] > 0.01f) break;
+        const float2 t0 = sc.triUV[3 * (size_t)hit.prim], t1 = sc.triUV[3 * (size_t)hit.prim + 1],
+                     t2 = sc.triUV[3 * (size_t)hit.prim + 2];
+        const float w0 = 1.0f - hit.beta - hit.gamma;
+        const float u = t1.x * hit.beta + t2.x * hit.gamma + t0.x * w0;   // triangleintersect.cu:36
+        const float v = t1.y * hit.beta + t2.y * hit.gamma + t0.y * w0;
+        Texel4 tl = tex_fetch(mat.lambert, sc.texPool, u, v);
+        Texel4 tp = tex_fetch(mat.phong, sc.texPool, u, v);
+        Texel4 te = tex_fetch(mat.exponent, sc.texPool, u, v);
+        V3 kd = v3(tl.x, tl.y, tl.z), ks = v3(tp.x, tp.y, tp.z);
+        float phongExponent = te.x;
+        float maxLambert = max_color(kd), maxPhong = max_color(ks);
+        if (maxLambert + maxPhong <= 0.000001f) break;
+
+        float pSelectLambert = det_div(maxLambert, maxPhong + maxLambert);
+        float chooseMaterial = det_min(xorwow_uniform(rng), 0.999999f);
+        const V3 recFlux = pflux;
+        float russian = russian_prob(pflux);
+        pflux /= russian;
+        bool done = (xorwow_uniform(rng) >= russian);
+        uint32_t recFlags = flag;
+        if (!done) {
+            if (chooseMaterial < pSelectLambert) {
+                pflux *= lambert_sample(&direction, &pdfW, ffNormal, kd, rng) / pSelectLambert;
+                recFlags = flag | EVPLP_FLAG_LAMBERT_ONLY;
+            } else {
+                pflux *= phong_sample(&direction, &pdfW, -rayDirection, geometryNormal, ks, phongExponent, rng) /
+                         (1.0f - pSelectLambert);
+                recFlags = flag | EVPLP_FLAG_PHONG_ONLY;
+            }
+            nextPosition = hitPosition;
+            nextDirection = direction;
+        }
+        store_record(rec + b, hitPosition, recFlags, ffNormal, pSelectLambert, recFlux, -rayDirection, kd, ks, phongExponent);
+        written = b + 1;
+        if (done) break;
+    }
+    // Slots after the end of the path: the reference clears only mFlags (lighttracing.cu:197-200);
+    // the whole record is zeroed here so that the buffer is a deterministic function of the inputs.
+    // NOTE: a path can leave a hole (bounce b rejected => loop ends), never a gap followed by data.
+    for (uint32_t b = written; b < B1; b++) zero_record(rec + b);
+    if (ovf) stats->stackOverflow = 1;
+    if (rays) atomicAdd(&stats->closestRays, rays);  // uniform address: ptxas aggregates per warp
+}
+
+// ------------------------------------------------------------------ VPL gather ----------
+constexpr int GATHER_BATCH = 32;   // VPL records staged per shared-memory batch
+constexpr int GATHER_WARPS = 8;
+
+struct GatherParams {
+    V3 cameraPosition;
+    unsigned misMode;
+    float pdfMc, clampingValue;
+    float invNumVpl;  // 1 / (float)numVplLightPaths
+    unsigned doAccumulate;
+    int x0, y0, x1, y1;  // tile
+    int W, H;
+    unsigned numChunks;  // VPL list split over gridDim.z
+    float vslRadius, vslInvPiRadius2;
+    unsigned numLightPaths, numVplLightPaths, B1;
+};
+
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf, const EvplpRecord* __restrict__ records,
+                  const uint32_t* __restrict__ vplList, const uint32_t* __restrict__ vplCount, long long* __restrict__ acc,
+                  DevStats* stats) {
+    __shared__ float4 batch[GATHER_BATCH * 6];
+    __shared__ uint32_t stacks[GATHER_WARPS][BVH_STACK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = gp.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = x < gp.x1 && y < gp.y1;
+    const size_t n = (size_t)gp.W * gp.H;
+    const size_t i = inside ? (size_t)y * gp.W + x : 0;
+    float gw;
+    Surface sf = load_surface(gbuf, n, i, &gw);
+    const bool valid = inside && gw != 0.0f;
+    const V3 wi01 = normalize(gp.cameraPosition - sf.pos);
+
+    const uint32_t total = *vplCount;
+    const uint32_t per = (total + gp.numChunks - 1) / gp.numChunks;
+    const uint32_t begin = min(total, blockIdx.z * per), end = min(total, begin + per);
+
+    V3 result = v3s(0.0f);
+    unsigned rays = 0;
+    int ovf = 0;
+    for (uint32_t base = begin; base < end; base += GATHER_BATCH) {
+        const uint32_t nb = min((uint32_t)GATHER_BATCH, end - base);
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < nb * 6; k += blockDim.x) {
+            const uint32_t r = vplList[base + k / 6];
+            batch[k] = reinterpret_cast<const float4*>(records + r)[k % 6];
+        }
+        __syncthreads();
+        for (uint32_t j = 0; j < nb; j++) {
+            const float4 a = batch[j * 6], b = batch[j * 6 + 1];
+            const V3 vpos = v3(a.x, a.y, a.z), vn = v3(b.x, b.y, b.z);
+            const V3 v12 = vpos - sf.pos;
+            const float c1 = det_max(dot(sf.normal, v12), 0.0f);
+            const float c2 = det_max(-dot(vn, v12), 0.0f);
+            const float c1c2 = c1 * c2;
+            const bool active = valid && !(c1c2 <= 0.000f);
+            rays += active ? 1u : 0u;
+            // Ray(vpl.pos, -v12, shadow, 0.0001, 1 - 0.0001) -- lighttracing.cu:292
+            const bool occluded = trace_any_warp(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
+            if (active && !occluded) {
+                const Vertex vp = load_vertex(&batch[j * 6]);
+                result += vpl_shade(sf, wi01, vp, v12, c1c2, gp.misMode, gp.pdfMc, gp.clampingValue);
+            }
+        }
+    }
+    if (ovf) stats->stackOverflow = 1;
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0 && rays) atomicAdd(&stats->shadowRays, (unsigned long long)rays);
+    if (!inside) return;
+    const V3 out = result * gp.invNumVpl;  // result / (float)numVplLightPaths (reciprocal multiply, lighttracing.cu:378)
+    const long long q[3] = {to_fixed(out.x), to_fixed(out.y), to_fixed(out.z)};
+    if (gp.numChunks == 1) {
+        for (int c = 0; c < 3; c++) acc[i * 3 + c] = gp.doAccumulate ? acc[i * 3 + c] + q[c] : q[c];
+    } else {
+        // (the tile was cleared beforehand when doAccumulate == 0)
+        for (int c = 0; c < 3; c++)
+            if (q[c]) atomicAdd(reinterpret_cast<unsigned long long*>(acc + i * 3 + c), (unsigned long long)q[c]);
+    }
+}
+
+__global__ void clear_tile_kernel(long long* acc, int W, int x0, int y0, int x1, int y1) {
+    int x = x0 + blockIdx.x * blockDim.x + threadIdx.x, y = y0 + blockIdx.y;
+    if (x >= x1 || y >= y1) return;
+    size_t i = (size_t)y * W + x;
+    acc[i * 3] = 0; acc[i * 3 + 1] = 0; acc[i * 3 + 2] = 0;
+}
+
+// ------------------------------------------------------------------ VSL gather ----------
+__device__ __forceinline__ V3 square_to_solid_angle(float sampleX, float sampleY, float halfAngleMax) {  // :382-390
+    const float phi = 2.0f * kPi * sampleX;
+    const float z = 1.0f - sampleY * (1.0f - det_cosf(halfAngleMax));
+    const float l = det_sqrtf(1.0f - z * z);
+    float s, c;
+    det_sincosf(phi, &s, &c);
+    return v3(c * l, s * l, z);
+}
+
+struct VslConsts {
+    float vslInvPiRadius2;
+};
+
+__device__ __forceinline__ float pdf_brdf1(const Surface& sf, V3 wi01, V3 w, float pSel) {
+    return lambert_pdf_w(sf.normal, w) * pSel + phong_pdf_w(sf.normal, w, wi01, sf.ks, sf.exponent) * (1.0f - pSel);
+}
+// quirk kept: no (1 - pSel) on the Phong term and the PIXEL's pSel (lighttracing.cu:440-441)
+__device__ __forceinline__ float pdf_brdf2(const Vertex& vp, V3 w, float pSel) {
+    return lambert_pdf_w(vp.normal, w) * pSel + phong_pdf_w(vp.normal, w, vp.fluxDir, vp.ks, vp.exponent);
+}
+
+__device__ V3 vsl_sample_cone(float K, float* misWeight, const Surface& sf, V3 wi01, const Vertex& vp, float halfCone,
+                              float solidAngle, float invSolidAngle, V3 nd12, Xorwow& rng) {  // :395-446
+    float maxLambert = max_color(sf.kd), maxPhong = max_color(sf.ks);
+    if (maxLambert + maxPhong <= 0.000001f) return v3s(0.0f);
+    float pSel = det_div(maxLambert, maxPhong + maxLambert);
+    (void)xorwow_uniform(rng);  // chooseMaterial (drawn, unused)
+    float sx = xorwow_uniform(rng);
+    float sy = xorwow_uniform(rng);
+    V3 wi12 = normalize(square_to_solid_angle(sx, sy, halfCone));
+    Onb onb = make_onb(nd12);
+    wi12 = onb_inverse_transform(onb, wi12);
+    wi12 = normalize(wi12);
+    const float cos1cos2 = det_max(dot(sf.normal, wi12), 0.0f) * det_max(-dot(vp.normal, wi12), 0.0f);
+    if (cos1cos2 <= 0.000000001f) return v3s(0.0f);
+    V3 brdf2 = kInvPi * vp.kd + phong_eval_f(-wi12, vp.fluxDir, vp.normal, vp.exponent) * vp.ks;
+    V3 brdf1 = kInvPi * sf.kd + phong_eval_f(wi01, wi12, sf.normal, sf.exponent) * sf.ks;
+    float pdfCone = invSolidAngle;
+    float p1 = pdf_brdf1(sf, wi01, wi12, pSel);
+    float p2 = pdf_brdf2(vp, -wi12, pSel);
+    *misWeight = det_div(pdfCone, p1 + p2 + pdfCone);
+    return vp.flux * K * cos1cos2 * brdf1 * brdf2 * solidAngle;
+}
+
+__device__ V3 vsl_sample_brdf1(float K, float* misWeight, const Surface& sf, V3 wi01, const Vertex& vp, float cosHalfCone,
+                               float invSolidAngle, V3 nd12, Xorwow& rng) {  // :448-521
+    float maxLambert = max_color(sf.kd), maxPhong = max_color(sf.ks);
+    if (maxLambert + maxPhong <= 0.000001f) return v3s(0.0f);
+    float pSel = det_div(maxLambert, maxPhong + maxLambert);
+    float chooseMaterial = det_min(xorwow_uniform(rng), 0.999999f);
+    V3 wi12, brdf1;
+    float pdfW;
+    if (chooseMaterial < pSel) {
+        brdf1 = lambert_sample(&wi12, &pdfW, sf.normal, sf.kd, rng) / pSel;
+    } else {
+        brdf1 = phong_sample(&wi12, &pdfW, wi01, sf.normal, sf.ks, sf.exponent, rng) / (1.0f - pSel);
+    }
+    if (dot(wi12, nd12) <= cosHalfCone) return v3s(0.0f);
+    const float cos1 = det_max(dot(sf.normal, wi12), 0.0f);
+    if (cos1 <= 0.000000001f) return v3s(0.0f);
+    const float cos2 = det_max(-dot(vp.normal, wi12), 0.0f);
+    V3 brdf2 = kInvPi * vp.kd + phong_eval_f(-wi12, vp.fluxDir, vp.normal, vp.exponent) * vp.ks;
+    (void)xorwow_uniform(rng);  // second chooseMaterial (drawn, unused)
+    float pdfCone = invSolidAngle;
+    float p1 = pdf_brdf1(sf, wi01, wi12, pSel);
+    float p2 = pdf_brdf2(vp, -wi12, pSel);
+    *misWeight = det_div(p1, p1 + p2 + pdfCone);
+    return vp.flux * K * cos2 * brdf1 * brdf2;
+}
+
+__device__ V3 vsl_sample_brdf2(float K, float* misWeight, const Surface& sf, V3 wi10, const Vertex& vp, float cosHalfCone,
+                               float invSolidAngle, V3 nd12, Xorwow& rng) {  // :523-594
+    V3 wi21, brdf2;
+    float pdfW;
+    {
+        float maxLambert = max_color(vp.kd), maxPhong = max_color(vp.ks);
+        if (maxLambert + maxPhong <= 0.000001f) return v3s(0.0f);
+        float pSelV = det_div(maxLambert, maxPhong + maxLambert);
+        float chooseMaterial = det_min(xorwow_uniform(rng), 0.999999f);
+        if (chooseMaterial < pSelV) {
+            brdf2 = lambert_sample(&wi21, &pdfW, vp.normal, vp.kd, rng) / pSelV;
+        } else {
+            brdf2 = phong_sample(&wi21, &pdfW, vp.fluxDir, vp.normal, vp.ks, vp.exponent, rng) / (1.0f - pSelV);
+        }
+    }
+    if (-dot(wi21, nd12) <= cosHalfCone) return v3s(0.0f);
+    V3 brdf1 = kInvPi * sf.kd + phong_eval_f(wi10, -wi21, sf.normal, sf.exponent) * sf.ks;
+    const float cos2 = det_max(dot(vp.normal, wi21), 0.0f);
+    if (cos2 <= 0.00000001f) return v3s(0.0f);
+    const float cos1 = det_max(-dot(sf.normal, wi21), 0.0f);
+    float maxLambert = max_color(sf.kd), maxPhong = max_color(sf.ks);
+    if (maxLambert + maxPhong <= 0.000001f) return v3s(0.0f);
+    float pSel = det_div(maxLambert, maxPhong + maxLambert);
+    (void)xorwow_uniform(rng);  // chooseMaterial (drawn, unused)
+    float pdfCone = invSolidAngle;
+    float p1 = pdf_brdf1(sf, wi10, -wi21, pSel);
+    float p2 = pdf_brdf2(vp, wi21, pSel);
+    *misWeight = det_div(p2, p1 + p2 + pdfCone);
+    return vp.flux * K * cos1 * brdf1 * brdf2;
+}
+
+// vslSplat after the shadow ray (lighttracing.cu:615-686)
+__device__ V3 vsl_shade(const GatherParams& gp, const Surface& sf, V3 wi10, const Vertex& vp, V3 v12, Xorwow& rng) {
+    float dist2 = dot(v12, v12);
+    float dist = det_sqrtf(dist2);
+    V3 nv12 = v12 / dist;
+    const float cos1cos2 = det_max(dot(sf.normal, nv12), 0.0f) * det_max(-dot(vp.normal, nv12), 0.0f);
+    if (cos1cos2 <= 0.000000001f) return v3s(0.0f);
+    const float rdratio = det_div(gp.vslRadius, dist);
+    const float halfCone = (rdratio >= 1.0f) ? det_div(kPi, 2.0f) : det_asinf(rdratio);
+    const float cosHalfCone = det_cosf(halfCone);
+    const float solidAngle = kPi * 2.0f * (1.0f - cosHalfCone);
+    const float invSolidAngle = det_div(1.0f, solidAngle);
+    V3 result = v3s(0.0f);
+    const int numSamples = (int)(det_div(halfCone, kPi) * 2.0f * 100.0f) + 1;
+    const float K = gp.vslInvPiRadius2;
+    for (int s = 0; s < numSamples; s++) {
+        float wc = 0.0f, w1 = 0.0f, w2 = 0.0f;
+        V3 rc = vsl_sample_cone(K, &wc, sf, wi10, vp, halfCone, solidAngle, invSolidAngle, nv12, rng);
+        V3 r1 = vsl_sample_brdf1(K, &w1, sf, wi10, vp, cosHalfCone, invSolidAngle, nv12, rng);
+        V3 r2 = vsl_sample_brdf2(K, &w2, sf, wi10, vp, cosHalfCone, invSolidAngle, nv12, rng);
+        result += wc * rc;
+        result += w1 * r1;
+        result += w2 * r2;
+    }
+    return result / (float)numSamples;
+}
+
+// splatSplotch (lighttracing.cu:689-722): one thread per pixel, the per-pixel XORWOW stream
+// runs through ALL VSLs in order, so the VSL list cannot be split.
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+gather_vsl_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ skip, const float4* __restrict__ gbuf,
+                  const EvplpRecord* __restrict__ records, const uint32_t* __restrict__ vplList,
+                  const uint32_t* __restrict__ vplCount, long long* __restrict__ acc, DevStats* stats) {
+    __shared__ uint32_t sm[kSkipMatrixWords];
+    __shared__ uint32_t stacks[GATHER_WARPS][BVH_STACK];
+    for (int k = threadIdx.x; k < kSkipMatrixWords; k += blockDim.x) sm[k] = skip[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = gp.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = x < gp.x1 && y < gp.y1;
+    const size_t n = (size_t)gp.W * gp.H;
+    const size_t i = inside ? (size_t)y * gp.W + x : 0;
+    float gw;
+    Surface sf = load_surface(gbuf, n, i, &gw);
+    const V3 wi10 = normalize(gp.cameraPosition - sf.pos);
+    Xorwow rng = xorwow_seed((uint32_t)i);  // curand_init(launchIndex.y * W + launchIndex.x, rngSeed, 0) -- :711
+    xorwow_apply_matrix(rng, sm);
+    const uint32_t total = *vplCount;
+    V3 result = v3s(0.0f);
+    unsigned rays = 0;
+    int ovf = 0;
+    for (uint32_t j = 0; j < total; j++) {
+        const float4* r = reinterpret_cast<const float4*>(records + vplList[j]);
+        const Vertex vp = load_vertex(r);
+        const V3 v12 = vp.pos - sf.pos;
+        rays += inside ? 1u : 0u;
+        // shadow ray FIRST, before the cosine test (lighttracing.cu:609-614)
+        const bool occluded = trace_any_warp(sc, inside, vp.pos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
+        if (inside && !occluded) result += vsl_shade(gp, sf, wi10, vp, v12, rng);
+    }
+    if (ovf) stats->stackOverflow = 1;
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0 && rays) atomicAdd(&stats->shadowRays, (unsigned long long)rays);
+    if (!inside) return;
+    const V3 out = result * gp.invNumVpl;
+    const long long q[3] = {to_fixed(out.x), to_fixed(out.y), to_fixed(out.z)};
+    for (int c = 0; c < 3; c++) acc[i * 3 + c] = gp.doAccumulate ? acc[i * 3 + c] + q[c] : q[c];
+}
+
+// LVC splatColor (lvclighttracing.cu:348-387): every pixel gathers from its own window of
+// light paths, so records are read straight from L2/HBM and rays are traced per lane.
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+gather_lvc_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ skip, const float4* __restrict__ gbuf,
+                  const EvplpRecord* __restrict__ records, long long* __restrict__ acc, DevStats* stats) {
+    __shared__ uint32_t sm[kSkipMatrixWords];
+    for (int k = threadIdx.x; k < kSkipMatrixWords; k += blockDim.x) sm[k] = skip[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = gp.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    if (!(x < gp.x1 && y < gp.y1)) return;
+    const size_t n = (size_t)gp.W * gp.H;
+    const size_t i = (size_t)y * gp.W + x;
+    float gw;
+    Surface sf = load_surface(gbuf, n, i, &gw);
+    unsigned long long rays = 0, pairs = 0;
+    V3 result = v3s(0.0f);
+    int ovf = 0;
+    if (gw != 0.0f) {
+        const V3 wi01 = normalize(gp.cameraPosition - sf.pos);
+        Xorwow rng = xorwow_seed((uint32_t)i);
+        xorwow_apply_matrix(rng, sm);
+        const unsigned lightPathOffset = (unsigned)(det_min(xorwow_uniform(rng), 0.999999f) * (float)gp.numLightPaths);
+        for (unsigned k = 0; k < gp.numVplLightPaths; k++) {
+            const unsigned lightPathId = (k + lightPathOffset) % gp.numLightPaths;
+            const size_t off = (size_t)lightPathId * gp.B1;
+            for (unsigned j = 0; j < gp.B1; j++) {
+                const float4* r = reinterpret_cast<const float4*>(records + off + j);
+                const float4 a = r[0];
+                if ((__float_as_uint(a.w) & EVPLP_FLAG_USABLE_VPL) == 0) continue;
+                pairs++;
+                const float4 b = r[1];
+                const V3 vpos = v3(a.x, a.y, a.z), vn = v3(b.x, b.y, b.z);
+                const V3 v12 = vpos - sf.pos;
+                const float c1c2 = det_max(dot(sf.normal, v12), 0.0f) * det_max(-dot(vn, v12), 0.0f);
+                if (c1c2 <= 0.000f) continue;
+                rays++;
+                if (trace_any(sc, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), &ovf)) continue;
+                const Vertex vp = load_vertex(r);
+                result += vpl_shade(sf, wi01, vp, v12, c1c2, gp.misMode, gp.pdfMc, gp.clampingValue);
+            }
+        }
+    }
+    if (ovf) stats->stackOverflow = 1;
+    if (rays) atomicAdd(&stats->shadowRays, rays);
+    if (pairs) atomicAdd(&stats->gatherPairs, pairs);
+    const V3 out = result * gp.invNumVpl;
+    const long long q[3] = {to_fixed(out.x), to_fixed(out.y), to_fixed(out.z)};
+    for (int c = 0; c < 3; c++) acc[i * 3 + c] = gp.doAccumulate ? acc[i * 3 + c] + q[c] : q[c];
+}
+
+// ------------------------------------------------------------------ photon splat --------
+struct SplatParams {
+    SplatUniforms U;
+    V3 camFwd, camRight, camUp;
+    float tanX, tanY, jx, jy;
+    int x0, y0, x1, y1, W, H;
+};
+
+// Conservative pixel rectangle of the sphere (p, r): only a cull; the exact test is the
+// per-texel |p - pos(x)|^2 <= r^2.
+__device__ __forceinline__ void splat_rect(const SplatParams& sp, V3 p, int* rx0, int* ry0, int* rx1, int* ry1) {
+    const double c0 = (double)p.x - sp.U.cameraPosition.x, c1 = (double)p.y - sp.U.cameraPosition.y,
+                 c2 = (double)p.z - sp.U.cameraPosition.z;
+    const double z = c0 * sp.camFwd.x + c1 * sp.camFwd.y + c2 * sp.camFwd.z;
+    const double xv = c0 * sp.camRight.x + c1 * sp.camRight.y + c2 * sp.camRight.z;
+    const double yv = c0 * sp.camUp.x + c1 * sp.camUp.y + c2 * sp.camUp.z;
+    const double rr = (double)sp.U.radius * 1.001 + 1e-6;
+    *rx0 = 0; *ry0 = 0; *rx1 = sp.W; *ry1 = sp.H;
+    if (z - rr <= 1e-4) return;
+    const double zn = z - rr, zf = z + rr;
+    {
+        const double a = xv - rr, b = xv + rr;
+        const double lo = fmin(a / zn, a / zf) / sp.tanX + sp.jx, hi = fmax(b / zn, b / zf) / sp.tanX + sp.jx;
+        const double plo = floor((lo + 1.0) * 0.5 * sp.W - 0.5) - 1.0, phi = ceil((hi + 1.0) * 0.5 * sp.W - 0.5) + 2.0;
+        *rx0 = (int)fmax(0.0, fmin((double)sp.W, plo));
+        *rx1 = (int)fmax(0.0, fmin((double)sp.W, phi));
+    }
+    {
+        const double a = yv - rr, b = yv + rr;
+        const double lo = fmin(a / zn, a / zf) / sp.tanY + sp.jy, hi = fmax(b / zn, b / zf) / sp.tanY + sp.jy;
+        const double plo = floor((lo + 1.0) * 0.5 * sp.H - 0.5) - 1.0, phi = ceil((hi + 1.0) * 0.5 * sp.H - 0.5) + 2.0;
+        *ry0 = (int)fmax(0.0, fmin((double)sp.H, plo));
+        *ry1 = (int)fmax(0.0, fmin((double)sp.H, phi));
+    }
+}
+
+// One warp per usable photon; lanes sweep the photon's screen rectangle and scatter-add
+// Q31.32 fixed-point contributions (order-independent => deterministic).
+__global__ void __launch_bounds__(256) splat_kernel(SplatParams sp, const float4* __restrict__ gbuf,
+                                                    const int32_t* __restrict__ gprim,
+                                                    const EvplpRecord* __restrict__ records,
+                                                    const uint32_t* __restrict__ photonList,
+                                                    const uint32_t* __restrict__ photonCount, long long* __restrict__ acc,
+                                                    DevStats* stats) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t total = *photonCount;
+    const size_t n = (size_t)sp.W * sp.H;
+    const float r2 = sp.U.radius * sp.U.radius;
+    unsigned frags = 0;
+    for (uint32_t w = warpId; w < total; w += numWarps) {
+        const uint32_t k = photonList[w];
+        const float4* r = reinterpret_cast<const float4*>(records + k);
+        const Vertex ph = load_vertex(r);
+        int rx0, ry0, rx1, ry1;
+        splat_rect(sp, ph.pos, &rx0, &ry0, &rx1, &ry1);
+        rx0 = max(rx0, sp.x0); ry0 = max(ry0, sp.y0); rx1 = min(rx1, sp.x1); ry1 = min(ry1, sp.y1);
+        const int rw = rx1 - rx0, rh = ry1 - ry0;
+        if (rw <= 0 || rh <= 0) continue;
+        const Vertex prev = load_vertex(r - 6);  // record k-1: same path (a photon is never a path's first record)
+        const int area = rw * rh;
+        for (int t = lane; t < area; t += 32) {
+            const int px = rx0 + t % rw, py = ry0 + t / rw;
+            const size_t i = (size_t)py * sp.W + px;
+            if (gprim[i] < 0) continue;
+            const float4 gp0 = gbuf[i];
+            const V3 d = ph.pos - v3(gp0.x, gp0.y, gp0.z);
+            if (dot(d, d) > r2) continue;
+            float gw;
+            const Surface sf = load_surface(gbuf, n, i, &gw);
+            V3 color;
+            if (!splat_fragment(sp.U, sf, ph, prev, &color)) continue;
+            frags++;
+            const long long q[3] = {to_fixed(color.x), to_fixed(color.y), to_fixed(color.z)};
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (q[c]) atomicAdd(reinterpret_cast<unsigned long long*>(acc + i * 3 + c), (unsigned long long)q[c]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
+    if (lane == 0 && frags) atomicAdd(&stats->splatFragments, (unsigned long long)frags);
+}
+
+// ------------------------------------------------------------------ light / resolve -----
+__global__ void light_pass_kernel(const int32_t* __restrict__ gprim, size_t n, int lightFirst, int lightCount,
+                                  uint32_t* __restrict__ light) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = gprim[i];
+    if (p >= lightFirst && p < lightFirst + lightCount) light[i] += 1;
+}
+
+struct ResolveParams {
+    float vplScale, photonScale, lightScale;
+    int gamma;
+    float lightDisplay[3];
+};
+
+__global__ void resolve_kernel(ResolveParams rp, const long long* __restrict__ vpl, const long long* __restrict__ photon,
+                               const uint32_t* __restrict__ light, size_t n, float* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool lit = light[i] != 0;
+    const float lightX = (lit ? rp.lightDisplay[0] : 0.f) * rp.lightScale;
+    const float stepv = (0.0f >= lightX) ? 1.0f : 0.0f;  // step(edge = lightColor.x, x = 0)  final.frag:26
+    for (int c = 0; c < 3; c++) {
+        float vplColor = (float)((double)vpl[i * 3 + c] * (1.0 / 4294967296.0)) * rp.vplScale;
+        float pmColor = (float)((double)photon[i * 3 + c] * (1.0 / 4294967296.0)) * rp.photonScale;
+        float lightColor = (lit ? rp.lightDisplay[c] : 0.f) * rp.lightScale;
+        float sum = stepv * (vplColor + pmColor) + lightColor;
+        out[i * 3 + c] = rp.gamma ? det_powf(sum, det_div(1.0f, 2.2f)) : sum;
+    }
+}
+
+// ------------------------------------------------------------------ list compaction -----
+struct FlagPred {
+    const EvplpRecord* records;
+    uint32_t mask;
+    __device__ bool operator()(uint32_t k) const { return (records[k].flags & mask) != 0; }
+};
+
+static cudaError_t compact_records(EvplpContext* c, uint64_t first, uint64_t count, uint32_t mask, DevBuf<uint32_t>& list,
+                                   uint32_t* devCount) {
+    cudaError_t e = list.reserve(count ? count : 1);
+    if (e != cudaSuccess) return e;
+    thrust::counting_iterator<uint32_t> it((uint32_t)first);
+    FlagPred pred{c->records.p, mask};
+    size_t tempBytes = 0;
+    e = cub::DeviceSelect::If(nullptr, tempBytes, it, list.p, devCount, (int)count, pred, c->stream);
+    if (e != cudaSuccess) return e;
+    e = c->sortTemp.reserve(tempBytes);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceSelect::If(c->sortTemp.p, tempBytes, it, list.p, devCount, (int)count, pred, c->stream);
+    c->launches += 2;
+    return e;
+}
+
+// ------------------------------------------------------------------ launchers -----------
+cudaError_t launch_gbuffer(EvplpContext* c) {
+    dim3 grid((c->W + 15) / 16, (c->H + 7) / 8);
+    gbuffer_kernel<<<grid, 128, 0, c->stream>>>(c->scene(), cam_of(c->params), c->W, c->H, c->gbuf.p, c->gprim.p, c->devStats.p);
+    c->launches++;
+    c->stats.closestRays += (uint64_t)c->W * c->H;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_light_trace(EvplpContext* c, uint32_t rngSeed, uint32_t firstPath, uint32_t numPaths) {
+    (void)rngSeed;
+    if (numPaths == 0) return cudaSuccess;
+    const uint32_t B1 = c->params.numPhotonsPerLightPath;
+    light_trace_kernel<<<(numPaths + 127) / 128, 128, 0, c->stream>>>(c->scene(), c->skipMatrix.p, c->records.p, firstPath,
+                                                                      numPaths, B1, c->devStats.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
+    const EvplpParams& P = c->params;
+    GatherParams g;
+    g.cameraPosition = v3p(P.cameraPosition);
+    g.misMode = P.misMode; g.pdfMc = P.pdfMc; g.clampingValue = P.clampingValue;
+    g.invNumVpl = 1.0f / (float)P.numVplLightPaths;
+    g.doAccumulate = P.doAccumulate;
+    g.x0 = t.x0; g.y0 = t.y0; g.x1 = t.x1; g.y1 = t.y1; g.W = c->W; g.H = c->H;
+    g.numChunks = 1;
+    g.vslRadius = P.vslRadius; g.vslInvPiRadius2 = P.vslInvPiRadius2;
+    g.numLightPaths = P.numLightPaths; g.numVplLightPaths = P.numVplLightPaths; g.B1 = P.numPhotonsPerLightPath;
+    return g;
+}
+
+extern int g_gatherChunks;  // capi.cu (0 = automatic)
+
+cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
+    const EvplpParams& P = c->params;
+    GatherParams g = gather_params(c, t);
+    const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
+    if (tw <= 0 || th <= 0) return cudaSuccess;
+    dim3 grid((tw + 15) / 16, (th + 15) / 16, 1);
+    cudaError_t e;
+    if (mode == EVPLP_GATHER_LVC) {
+        gather_lvc_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->skipMatrix.p, c->gbuf.p, c->records.p,
+                                                                      c->accVpl.p, c->devStats.p);
+        c->launches++;
+        return cudaGetLastError();
+    }
+    // usable VPLs of the record prefix, in order
+    const uint64_t prefix = (uint64_t)P.numPhotonsPerLightPath * P.numVplLightPaths;
+    uint32_t* devCount = c->counters.p + 3;
+    e = compact_records(c, 0, prefix, EVPLP_FLAG_USABLE_VPL, c->vplList, devCount);
+    if (e != cudaSuccess) return e;
+    uint32_t count = 0;
+    e = cudaMemcpyAsync(&count, devCount, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return e;
+    c->stats.gatherPairs += (uint64_t)count * (uint64_t)tw * th;
+    if (mode == EVPLP_GATHER_VSL) {
+        gather_vsl_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->skipMatrix.p, c->gbuf.p, c->records.p,
+                                                                      c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+        c->launches++;
+        return cudaGetLastError();
+    }
+    // split the VPL list over gridDim.z when the tile alone cannot fill the GPU
+    unsigned chunks = 1;
+    if (g_gatherChunks > 0) {
+        chunks = (unsigned)g_gatherChunks;
+    } else {
+        const unsigned blocks = grid.x * grid.y;
+        const unsigned want = 148u * 4u;
+        if (blocks < want) chunks = (want + blocks - 1) / blocks;
+        const unsigned maxChunks = (count + 4 * GATHER_BATCH - 1) / (4 * GATHER_BATCH);
+        if (chunks > maxChunks) chunks = maxChunks ? maxChunks : 1;
+    }
+    g.numChunks = chunks;
+    grid.z = chunks;
+    if (chunks > 1 && !P.doAccumulate) {
+        dim3 cg((tw + 127) / 128, th);
+        clear_tile_kernel<<<cg, 128, 0, c->stream>>>(c->accVpl.p, c->W, t.x0, t.y0, t.x1, t.y1);
+        c->launches++;
+    }
+    gather_vpl_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount,
+                                                                  c->accVpl.p, c->devStats.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numRecords, EvplpTile t) {
+    const EvplpParams& P = c->params;
+    if (numRecords == 0) return cudaSuccess;
+    uint32_t* devCount = c->counters.p + 3;
+    cudaError_t e = compact_records(c, firstRecord, numRecords, EVPLP_FLAG_USABLE_PHOTON, c->photonList, devCount);
+    if (e != cudaSuccess) return e;
+    uint32_t count = 0;
+    e = cudaMemcpyAsync(&count, devCount, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return e;
+    c->stats.splatPhotons += count;
+    if (count == 0 || !(P.radius > 0.0f)) return cudaSuccess;  // radiusPercentage 0 => degenerate spheres, no fragments
+    SplatParams sp;
+    sp.U.cameraPosition = v3p(P.cameraPosition);
+    sp.U.radius = P.radius; sp.U.pdfMc = P.pdfMc; sp.U.clampingValue = P.clampingValue;
+    sp.U.misMode = P.misMode; sp.U.numLightPaths = P.numLightPaths;
+    sp.camFwd = v3p(P.camForward); sp.camRight = v3p(P.camRight); sp.camUp = v3p(P.camUp);
+    sp.tanX = P.tanHalfFovX; sp.tanY = P.tanHalfFovY; sp.jx = P.jitter[0]; sp.jy = P.jitter[1];
+    sp.x0 = t.x0; sp.y0 = t.y0; sp.x1 = t.x1; sp.y1 = t.y1; sp.W = c->W; sp.H = c->H;
+    const uint32_t warpsWanted = count;
+    uint32_t blocks = (warpsWanted + 7) / 8;
+    const uint32_t maxBlocks = 148u * 8u * 4u;
+    if (blocks > maxBlocks) blocks = maxBlocks;
+    splat_kernel<<<blocks, 256, 0, c->stream>>>(sp, c->gbuf.p, c->gprim.p, c->records.p, c->photonList.p, devCount,
+                                                c->accPhoton.p, c->devStats.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_light_pass(EvplpContext* c) {
+    const size_t n = (size_t)c->W * c->H;
+    light_pass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->gprim.p, n, c->lightFirst, c->lightCount, c->accLight.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(EvplpContext* c, float vplScale, float photonScale, float lightScale, int gamma) {
+    const size_t n = (size_t)c->W * c->H;
+    ResolveParams rp;
+    rp.vplScale = vplScale; rp.photonScale = photonScale; rp.lightScale = lightScale; rp.gamma = gamma;
+    for (int k = 0; k < 3; k++) rp.lightDisplay[k] = c->lightDisplay[k];
+    resolve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(rp, c->accVpl.p, c->accPhoton.p, c->accLight.p, n, c->resolveOut.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ debug taps ----------
+__global__ void trace_rays_kernel(DevScene sc, const float* __restrict__ rays, uint64_t n, int anyHit, int32_t* outPrim,
+                                  float* outT, DevStats* stats) {
+    __shared__ uint32_t stacks[4][BVH_STACK];
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    const float* r = rays + (live ? i : 0) * 8;
+    V3 o = v3(r[0], r[1], r[2]), d = v3(r[3], r[4], r[5]);
+    int ovf = 0;
+    if (anyHit == 2) {  // warp-cooperative any-hit (the gather's traversal)
+        bool occ = trace_any_warp(sc, live, o, d, r[6], r[7], stacks[threadIdx.x >> 5], &ovf);
+        if (live) { outPrim[i] = occ ? 1 : 0; if (outT) outT[i] = 0.f; }
+    } else if (live) {
+        if (anyHit) {
+            outPrim[i] = trace_any(sc, o, d, r[6], r[7], &ovf) ? 1 : 0;
+            if (outT) outT[i] = 0.f;
+        } else {
+            RayHit h = trace_closest(sc, o, d, r[6], r[7], &ovf);
+            outPrim[i] = h.prim;
+            if (outT) outT[i] = h.prim >= 0 ? h.t : 0.f;
+        }
+    }
+    if (ovf) stats->stackOverflow = 1;
+}
+
+cudaError_t launch_trace_rays(EvplpContext* c, const float* devRays, uint64_t n, int anyHit, int32_t* devPrim, float* devT) {
+    if (n == 0) return cudaSuccess;
+    trace_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene(), devRays, n, anyHit, devPrim, devT, c->devStats.p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+__global__ void debug_uniforms_kernel(const uint32_t* __restrict__ skip, uint32_t seed, uint32_t n, float* out) {
+    __shared__ uint32_t sm[kSkipMatrixWords];
+    for (int k = threadIdx.x; k < kSkipMatrixWords; k += blockDim.x) sm[k] = skip[k];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    Xorwow rng = xorwow_seed(seed);
+    xorwow_apply_matrix(rng, sm);
+    for (uint32_t i = 0; i < n; i++) out[i] = xorwow_uniform(rng);
+}
+
+cudaError_t launch_debug_uniforms(EvplpContext* c, uint32_t seed, uint32_t n, float* devOut) {
+    debug_uniforms_kernel<<<1, 128, 0, c->stream>>>(c->skipMatrix.p, seed, n, devOut);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// The real cuRAND device API, exactly as the reference calls it (lighttracing.cu:202-203):
+// pins the oracle's and the product's XORWOW restatements against cuRAND itself.
+__global__ void debug_curand_kernel(uint32_t seed, uint32_t subsequence, uint32_t n, float* out) {
+    curandState st;
+    curand_init(seed, subsequence, 0, &st);
+    for (uint32_t i = 0; i < n; i++) out[i] = curand_uniform(&st);
+}
+
+cudaError_t launch_debug_curand(EvplpContext* c, uint32_t seed, uint32_t subsequence, uint32_t n, float* devOut) {
+    debug_curand_kernel<<<1, 1, 0, c->stream>>>(seed, subsequence, n, devOut);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+__global__ void debug_math_kernel(int op, const float* x, const float* y, uint32_t n, float* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (op) {
+        case 0: out[i] = det_sinf(x[i]); break;
+        case 1: out[i] = det_cosf(x[i]); break;
+        case 2: out[i] = det_powf(x[i], y[i]); break;
+        case 3: out[i] = det_asinf(x[i]); break;
+        case 4: out[i] = det_sqrtf(x[i]); break;
+        default: out[i] = 0.f;
+    }
+}
+
+cudaError_t launch_debug_math(EvplpContext* c, int op, const float* x, const float* y, uint32_t n, float* out) {
+    if (n == 0) return cudaSuccess;
+    debug_math_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(op, x, y, n, out);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace evplp

@@ -225,6 +225,10 @@ int evplp_trace_rays(evplp_handle h, const float* rays, uint64_t numRays, int an
 int evplp_download_accum(evplp_handle h, int64_t* vpl, int64_t* photon, uint32_t* light);
 /* First n cuRAND-compatible uniforms of stream (seed, subsequence) produced on the device. */
 int evplp_debug_uniforms(evplp_handle h, uint32_t seed, uint32_t subsequence, uint32_t n, float* out);
+/* The same stream from the REAL cuRAND device API, called exactly as the reference does
+ * (curand_init(seed, subsequence, 0, &state); curand_uniform(&state) -- lighttracing.cu:202-203).
+ * Pins the XORWOW restatements (product and oracle) against cuRAND itself. */
+int evplp_debug_curand(evplp_handle h, uint32_t seed, uint32_t subsequence, uint32_t n, float* out);
 /* detmath on device: op 0 sin, 1 cos, 2 pow(x,y), 3 asin, 4 sqrt; x,y,out are n floats */
 int evplp_debug_math(evplp_handle h, int op, const float* x, const float* y, uint32_t n, float* out);
 int evplp_stats(evplp_handle h, EvplpStats* stats);
@@ -235,6 +239,10 @@ int evplp_last_stage_ms(evplp_handle h, int stage, float* ms);
 int evplp_synchronize(evplp_handle h);
 /* Number of kernel launches issued by this handle since creation (bench.py gpu_launches). */
 int evplp_launch_count(evplp_handle h, uint64_t* count);
+/* Tuning knobs (no reference counterpart).  "gather_chunks": number of slices the VPL list is
+ * split into across thread blocks (0 = automatic; 1 = every pixel sums its VPLs in record
+ * order in one thread, which makes the gather bit-identical to the scalar oracle). */
+int evplp_set_option(evplp_handle h, const char* name, int value);
 
 #ifdef __cplusplus
 }
