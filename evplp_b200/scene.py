@@ -241,5 +241,5 @@ def cornell_scene(seed=1, detail=4, glossy=True, light_exponent=0.0, light_grid=
     # ceiling light: light_grid x light_grid quads, facing down
     v, i, _ = _grid((3.5, 6.5, Zh - 0.02), (3.0, 0, 0), (0, -3.0, 0), light_grid, light_grid)
     sc.add_area_light(v, i, (17.0, 12.0, 4.0, light_exponent))
-    cam = dict(origin=(5.0, 0.3, 3.0), lookat=(5.0, 9.0, 4.5), up=(0, 0, 1), fovx=70.0)
+    cam = dict(origin=(5.0, 0.3, 3.0), lookat=(5.0, 9.0, 6.0), up=(0, 0, 1), fovx=70.0)
     return sc, cam
