@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) light_trace_kernel(DevScene sc, const uin
 }
 
 // ------------------------------------------------------------------ VPL gather ----------
-constexpr int GATHER_BATCH = 32;   // VPL records staged per shared-memory batch
+constexpr int GATHER_BATCH = 128;   // VPL records staged per shared-memory batch
 constexpr int GATHER_WARPS = 8;
 
 struct GatherParams {
@@ -531,7 +531,7 @@ gather_lvc_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ ski
 struct SplatParams {
     SplatUniforms U;
     V3 camFwd, camRight, camUp;
-    float tanX, tanY, jx, jy;
+    float tanX, tanY, jx, jy, nearD;
     int x0, y0, x1, y1, W, H;
 };
 
@@ -544,9 +544,11 @@ __device__ __forceinline__ void splat_rect(const SplatParams& sp, V3 p, int* rx0
     const double xv = c0 * sp.camRight.x + c1 * sp.camRight.y + c2 * sp.camRight.z;
     const double yv = c0 * sp.camUp.x + c1 * sp.camUp.y + c2 * sp.camUp.z;
     const double rr = (double)sp.U.radius * 1.001 + 1e-6;
-    *rx0 = 0; *ry0 = 0; *rx1 = sp.W; *ry1 = sp.H;
-    if (z - rr <= 1e-4) return;
-    const double zn = z - rr, zf = z + rr;
+    // G-buffer points lie at depth z >= nearDist along the forward axis (primary rays start at tmin = nearDist)
+    const double zNear = (double)sp.nearD * 0.999;
+    *rx0 = 0; *ry0 = 0; *rx1 = 0; *ry1 = 0;
+    if (z + rr < zNear) return;  // sphere entirely behind the near plane: no texel can be inside it
+    const double zn = fmax(z - rr, zNear), zf = z + rr;
     {
         const double a = xv - rr, b = xv + rr;
         const double lo = fmin(a / zn, a / zf) / sp.tanX + sp.jx, hi = fmax(b / zn, b / zf) / sp.tanX + sp.jx;
@@ -772,7 +774,7 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
     sp.U.radius = P.radius; sp.U.pdfMc = P.pdfMc; sp.U.clampingValue = P.clampingValue;
     sp.U.misMode = P.misMode; sp.U.numLightPaths = P.numLightPaths;
     sp.camFwd = v3p(P.camForward); sp.camRight = v3p(P.camRight); sp.camUp = v3p(P.camUp);
-    sp.tanX = P.tanHalfFovX; sp.tanY = P.tanHalfFovY; sp.jx = P.jitter[0]; sp.jy = P.jitter[1];
+    sp.tanX = P.tanHalfFovX; sp.tanY = P.tanHalfFovY; sp.jx = P.jitter[0]; sp.jy = P.jitter[1]; sp.nearD = P.nearDist;
     sp.x0 = t.x0; sp.y0 = t.y0; sp.x1 = t.x1; sp.y1 = t.y1; sp.W = c->W; sp.H = c->H;
     const uint32_t warpsWanted = count;
     uint32_t blocks = (warpsWanted + 7) / 8;

@@ -1,0 +1,148 @@
+// host_capi.cpp -- C entry points over the C++ host classes, for ctypes callers (tests, bench.py).
+// No compute happens here: scene generation / loading is host data preparation and every
+// render call goes through libevplp_b200.so.
+#include <cstring>
+#include "rtcomphoton.h"
+#include "scenegen.h"
+
+using namespace evplp_host;
+
+static thread_local std::string g_hostErr;
+
+struct HostScene {
+    shared_ptr<RtScene> scene;
+    std::vector<EvplpMeshDesc> md;
+    std::vector<EvplpMaterialDesc> mt;
+};
+
+struct HostTechnique {
+    std::unique_ptr<RtComPhoton> tech;
+    shared_ptr<RtScene> scene;
+};
+
+#define GUARD(...) try { __VA_ARGS__ } catch (const std::exception& e) { g_hostErr = e.what(); return -1; }
+
+extern "C" {
+
+const char* evplp_host_last_error(void) { return g_hostErr.c_str(); }
+
+// Write the procedural stand-in of a named reference scene (OBJ + MTL + PPM + technique JSONs).
+int evplp_host_export_scene(const char* name, const char* outDir, uint32_t seed, int detail, int resX, int resY) {
+    GUARD(GenScene g = GenerateNamed(name, seed, detail); ExportScene(g, outDir, resX, resY); return 0;)
+}
+
+// Build the same scene in memory (identical triangles / materials to loading the exported files).
+void* evplp_host_generate_scene(const char* name, uint32_t seed, int detail, float aspect) {
+    try {
+        auto* hs = new HostScene();
+        hs->scene = ToRtScene(GenerateNamed(name, seed, detail), aspect);
+        hs->scene->descriptors(hs->md, hs->mt);
+        return hs;
+    } catch (const std::exception& e) { g_hostErr = e.what(); return nullptr; }
+}
+
+// LoadScene(json) (main.cpp:42-85)
+void* evplp_host_load_scene(const char* jsonPath) {
+    try {
+        Json json = Json::parse_file(jsonPath);
+        auto* hs = new HostScene();
+        hs->scene = LoadScene(json, jsonPath);
+        if (!hs->scene) throw std::runtime_error("no scene in json");
+        hs->scene->descriptors(hs->md, hs->mt);
+        return hs;
+    } catch (const std::exception& e) { g_hostErr = e.what(); return nullptr; }
+}
+
+void evplp_host_scene_destroy(void* s) { delete (HostScene*)s; }
+
+// Descriptor views (valid while the scene lives): the same structs evplp_upload_scene takes.
+int evplp_host_scene_descriptors(void* s, const EvplpMeshDesc** meshes, int32_t* numMeshes, const EvplpMaterialDesc** materials,
+                                 int32_t* numMaterials, int32_t* lightMeshIndex, float lightPre[4], float lightDisplay[4]) {
+    HostScene* hs = (HostScene*)s;
+    *meshes = hs->md.data(); *numMeshes = (int32_t)hs->md.size();
+    *materials = hs->mt.data(); *numMaterials = (int32_t)hs->mt.size();
+    *lightMeshIndex = hs->scene->lightMeshIndex();
+    const Vec4& p = hs->scene->mArealight->mPrecomputedLightIntensity;
+    const Vec4& d = hs->scene->mArealight->mLightIntensity;
+    lightPre[0] = p.x; lightPre[1] = p.y; lightPre[2] = p.z; lightPre[3] = p.w;
+    lightDisplay[0] = d.x; lightDisplay[1] = d.y; lightDisplay[2] = d.z; lightDisplay[3] = d.w;
+    return 0;
+}
+
+// scalars: [0] bounding-sphere radius, [1] total area, [2] number of triangles; camera: origin, f, s, u, tanX, tanY (14 floats)
+int evplp_host_scene_info(void* s, float scalars[3], float camera[14]) {
+    GUARD(
+        HostScene* hs = (HostScene*)s;
+        scalars[0] = hs->scene->findBoundingSphereRadius();
+        scalars[1] = hs->scene->totalArea();
+        scalars[2] = (float)hs->scene->numTriangles();
+        Vec3 f, sv, u; float tx, ty;
+        hs->scene->mCamera->basis(&f, &sv, &u, &tx, &ty);
+        Vec3 o = hs->scene->mCamera->getOrigin();
+        const float c[14] = {o.x, o.y, o.z, f.x, f.y, f.z, sv.x, sv.y, sv.z, u.x, u.y, u.z, tx, ty};
+        memcpy(camera, c, sizeof(c));
+        return 0;
+    )
+}
+
+// RtComPhoton / RtLvcComPhoton over a scene; `techniqueJson` is the text of the "photonfam" object.
+void* evplp_host_technique_create(void* s, const char* techniqueJson, int resX, int resY, int device, int lvc, int rank, int worldSize) {
+    try {
+        HostScene* hs = (HostScene*)s;
+        auto* ht = new HostTechnique();
+        ht->scene = hs->scene;
+        ht->tech.reset(lvc ? new RtLvcComPhoton(device) : new RtComPhoton(device));
+        ht->tech->setPartition(rank, worldSize);
+        ht->tech->setWriteOutputs(false);
+        Vec2 res; res.x = (float)resX; res.y = (float)resY;
+        ht->tech->parse(ht->scene, res, Json::parse(techniqueJson));
+        ht->tech->setup();
+        return ht;
+    } catch (const std::exception& e) { g_hostErr = e.what(); return nullptr; }
+}
+
+void* evplp_host_technique_handle(void* t) { return ((HostTechnique*)t)->tech->handle(); }
+
+// one pass of the per-iteration loop body; returns 1 to continue, 0 when the loop ends, -1 on error
+int evplp_host_technique_iterate(void* t) {
+    GUARD(return ((HostTechnique*)t)->tech->iterate() ? 1 : 0;)
+}
+
+// state: photonRadius, clampingValue, pdfMc, vslRadius, vslInvPiRadius2, numIterations
+int evplp_host_technique_state(void* t, float state[6]) {
+    RtComPhoton* c = ((HostTechnique*)t)->tech.get();
+    state[0] = c->mPhotonRadius; state[1] = c->mClampingValue; state[2] = c->mPrecomptedPdfMc; state[3] = c->mVslRadius;
+    state[4] = c->mVslInvPiRadius2; state[5] = (float)c->numIterations();
+    return 0;
+}
+
+// resolve like the display path (runFinalProgram(param, param, 1, gamma)); rows bottom-up
+int evplp_host_technique_final(void* t, float vplScale, float photonScale, float lightScale, int gamma, float* hostRGB) {
+    GUARD(
+        FloatImage img = ((HostTechnique*)t)->tech->runFinalProgram(vplScale, photonScale, lightScale, gamma != 0);
+        memcpy(hostRGB, img.data(), sizeof(float) * 3 * img.width() * img.height());
+        return 0;
+    )
+}
+
+void evplp_host_technique_destroy(void* t) { delete (HostTechnique*)t; }
+
+// The whole blocking call of the reference: RtTechnique::render(scene, resolution, json) + outputs.
+int evplp_host_render_json(const char* jsonPath, int device) {
+    GUARD(
+        Json json = Json::parse_file(jsonPath);
+        shared_ptr<RtScene> scene = LoadScene(json, jsonPath);
+        if (!scene) throw std::runtime_error("no scene in json");
+        Vec2 res; res.x = json["resX"].as_float(); res.y = json["resY"].as_float();
+        if (!json["photonfam"].is_null()) { RtComPhoton t(device); t.render(scene, res, json["photonfam"]); }
+        if (!json["lvcphotonfam"].is_null()) { RtLvcComPhoton t(device); t.render(scene, res, json["lvcphotonfam"]); }
+        return 0;
+    )
+}
+
+float evplp_host_pfm_relmse(const char* a, const char* b) {
+    try { return FloatImage::ComputeRelMse(FloatImage::LoadPFM(a), FloatImage::LoadPFM(b)); }
+    catch (const std::exception& e) { g_hostErr = e.what(); return -1.f; }
+}
+
+}  // extern "C"

@@ -1,0 +1,330 @@
+// rtcomphoton.h -- RtComPhoton / RtLvcComPhoton: the EVPLP technique, headless, over the C ABI.
+//
+// Mirrors reflectcuts/realtimetechniques/rtcomphoton/rtcomphoton.h (and rtlvccomphoton.h):
+// same JSON keys (:114-218), same per-iteration order and stage names (:936-1068), same
+// progressive schedule (:1033-1063), same three PFM outputs + stat JSON (:1107-1132).  The
+// OptiX programs / GL passes behind each run*() member are the sm_100a kernels of
+// libevplp_b200.so.  New here (the reference is single-GPU): setPartition(rank, worldSize)
+// renders iterations k = rank (mod worldSize) and evplp_reduce() sums the accumulation layers.
+#pragma once
+#include <chrono>
+#include <cmath>
+#include <functional>
+#include <iomanip>
+#include <random>
+#include "floatimage.h"
+#include "rttechnique.h"
+
+namespace evplp_host {
+
+// IndependentSampler over std::mt19937 (sampler/independent.h:37-40, common/rng.h:14-40).
+// nextFloat() = uniform_real_distribution<float>(0,1): defined here as float(u32) * 2^-32 with the
+// "== 1" guard; nextVec2() draws x first (both unpinned in the reference).
+class IndependentSampler {
+public:
+    explicit IndependentSampler(uint32_t seed) : mGen(seed) {}
+    float nextFloat() {
+        float u = (float)mGen() * 2.3283064365386963e-10f;
+        if (u >= 1.0f) u = std::nextafter(1.0f, 0.0f);
+        return u;
+    }
+    Vec2 nextVec2() { Vec2 v; v.x = nextFloat(); v.y = nextFloat(); return v; }
+private:
+    std::mt19937 mGen;
+};
+
+class StopWatch {  // common/stopwatch.h:6-30
+public:
+    StopWatch() { reset(); }
+    void reset() { mStart = std::chrono::steady_clock::now(); }
+    float timeMilliSec() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - mStart).count(); }
+private:
+    std::chrono::steady_clock::time_point mStart;
+};
+
+class RtComPhoton : public RtTechnique {
+public:
+    enum EFrame { ClearEveryFrame = 0, Accumulate = 1 };
+    enum EMis { One = 0, Balance, Max, Power2, GeometryClamp, GeometryBrdfClamp };
+
+    explicit RtComPhoton(int device = 0, int gatherMode = EVPLP_GATHER_VPL) : mDevice(device), mBaseGatherMode(gatherMode) {}
+    ~RtComPhoton() override { destroy(); }
+
+    void setPartition(int rank, int worldSize) { mRank = rank; mWorldSize = worldSize; }
+    void setNcclComm(void* comm) { mNcclComm = comm; }
+    void setWriteOutputs(bool w) { mWriteOutputs = w; }
+
+    static EMis misFromString(const std::string& s) {
+        static const std::map<std::string, EMis> m = {{"one", One}, {"balance", Balance}, {"max", Max}, {"power2", Power2},
+                                                      {"geometryClamp", GeometryClamp}, {"geometryBrdfClamp", GeometryBrdfClamp}};
+        auto it = m.find(s);
+        if (it == m.end()) throw std::runtime_error("unknown misMode " + s);
+        return it->second;
+    }
+
+    // rtcomphoton.h:107-223
+    void parse(shared_ptr<RtScene>& scene, const Vec2& resolution, const Json& json) {
+        mScene = scene;
+        mResolution = resolution;
+        mInvResolution.x = 1.0f / resolution.x; mInvResolution.y = 1.0f / resolution.y;
+        mNumLightPaths = (uint32_t)json.at("numLightPaths").as_int();
+        mNumVplLightPaths = (uint32_t)json.at("numVplLightPaths").as_int();
+        mNumMaxBounce = (uint32_t)json.at("numMaxBounces").as_int();
+        mNumPhotonsPerLightPath = mNumMaxBounce + 1;
+        mRadiusPercentage = json.at("radiusPercentage").as_float();
+        mPhotonRadius = mScene->findBoundingSphereRadius() * mRadiusPercentage;
+        mPrecomptedPdfMc = static_cast<float>(mNumVplLightPaths) / static_cast<float>(mNumLightPaths) * Math::InvPi / (mPhotonRadius * mPhotonRadius);
+        mDoWriteEveryFrame = json.contains("writeEveryFrame") ? json["writeEveryFrame"].as_bool() : false;
+        mNumMaxIteration = json.at("numMaxIteration").as_int();
+        mTimelimitMs = json.at("timeLimitMs").as_float();
+        const std::string frameMode = json.at("frameMode").as_string();
+        if (frameMode == "accumulate") mFrameMode = Accumulate;
+        else if (frameMode == "cleareveryframe") mFrameMode = ClearEveryFrame;
+        else throw std::runtime_error("unknown frameMode " + frameMode);
+        mMisMode = json.contains("misMode") ? misFromString(json["misMode"].as_string()) : Balance;
+        if (json.contains("clampingStart")) throw std::runtime_error("clampingStart option is not use anymore; remove it from your JSON file");
+        if (json.contains("targetRenderingTime")) mTargetRenderingTime = json["targetRenderingTime"].as_float();
+        if (!json.contains("clampingCoeff")) {
+            float totalArea = scene->totalArea();
+            std::cout << "Total area computation: " << totalArea << "\n";
+            mClampingValue = 1.f / totalArea;
+            mClampingStart = 1.f / totalArea;
+        } else {
+            float clampCoeff = json["clampingCoeff"].as_float();
+            mClampingValue = clampCoeff;
+            mClampingStart = clampCoeff;
+        }
+        mRngOffset = (uint32_t)json.at("rngOffset").as_int();
+        mDumpCombineFilename = json.at("combinedFilename").as_string();
+        mDumpWeightedPhotonFilename = json.at("weightedPhotonFilename").as_string();
+        mDumpWeightedVplFilename = json.at("weightedVplFilename").as_string();
+        mStatFilename = json.at("statFilename").as_string();
+        mJitter = json.at("useJitter").as_bool();
+        mUseStat = json.at("useStat").as_bool();
+        if (json.contains("DoProgressive")) mDoProgressive = json["DoProgressive"].as_bool();
+        if (json.contains("AlphaProgressive")) mAlphaProgressive = json["AlphaProgressive"].as_float();
+        if (json.contains("run")) {
+            const Json& r = json["run"];
+            if (r.contains("deferredShading")) mDoDeferredShading = r["deferredShading"].as_bool();
+            if (r.contains("lightTracing")) mDoLightTracing = r["lightTracing"].as_bool();
+            if (r.contains("vplSplat")) mDoVplSplat = r["vplSplat"].as_bool();
+            if (r.contains("photonSplat")) mDoPhotonSplat = r["photonSplat"].as_bool();
+            if (r.contains("lightRender")) mDoLightRender = r["lightRender"].as_bool();
+            if (r.contains("finalize")) mDoFinalize = r["finalize"].as_bool();
+        }
+        if (mNumVplLightPaths == 0) {
+            std::cout << "WARN: 0 VPL light paths. Disable mDoVplSplat\n";
+            mDoVplSplat = false;
+        }
+        if (json.contains("forceVsl")) {
+            mForceVsl = json["forceVsl"].as_bool();
+            if (mForceVsl) {
+                mVslRadiusPercentage = json.at("vslRadiusPercentage").as_float();
+                mVslRadius = mScene->findBoundingSphereRadius() * mVslRadiusPercentage;
+                if (mVslRadius <= 0.008) {
+                    mVslRadius = std::max(mVslRadius, 0.008f);
+                    std::cout << "warning : vslRadius is too small. clamped vslRadius" << std::endl;
+                }
+                mVslInvPiRadius2 = Math::InvPi / (mVslRadius * mVslRadius);
+            }
+        }
+    }
+
+    void render(shared_ptr<RtScene>& scene, const Vec2& resolution, const Json& json) override {
+        parse(scene, resolution, json);
+        setup();
+        run();
+        destroy();
+    }
+
+    // rtcomphoton.h:646-708: context, scene upload, acceleration structure
+    void setup() {
+        check(evplp_create(mDevice, (int)mResolution.x, (int)mResolution.y, &mHandle), "evplp_create");
+        check(mScene->upload(mHandle), "evplp_upload_scene");
+        check(evplp_build_bvh(mHandle), "evplp_build_bvh");
+        mScene->mCamera->basis(&mCamF, &mCamS, &mCamU, &mTanHalfX, &mTanHalfY);
+        mMainSampler.reset(new IndependentSampler(mRngOffset));
+        mNumIterations = 0;
+        check(evplp_clear_accum(mHandle), "evplp_clear_accum");
+        mMasterWatch.reset();
+        mPrevTiming = 0.f;
+    }
+
+    // ---- the per-iteration stages (reference member names) ----
+    void runDeferredProgram() { check(evplp_gbuffer(mHandle), "evplp_gbuffer"); }                     // :710-754
+    void runOptixLightTracingProgram(uint32_t rngSeed) {                                                // :869-881
+        check(evplp_light_trace(mHandle, rngSeed, 0, mNumLightPaths), "evplp_light_trace");
+    }
+    void runOptixVplProgram() {                                                                         // :857-867
+        const int mode = mForceVsl ? EVPLP_GATHER_VSL : mBaseGatherMode;
+        check(evplp_vpl_gather(mHandle, nullptr, mode), "evplp_vpl_gather");
+    }
+    void runPhotonSplat() {                                                                             // :789-837
+        check(evplp_photon_splat(mHandle, 0, (uint64_t)mNumLightPaths * mNumPhotonsPerLightPath, nullptr), "evplp_photon_splat");
+    }
+    void runLightProgram() { check(evplp_light_pass(mHandle), "evplp_light_pass"); }                    // :839-855
+    FloatImage runFinalProgram(float vplScale, float photonScale, float lightScale, bool gamma) {        // :756-787 + dumpImage :225-249
+        FloatImage img((size_t)mResolution.x, (size_t)mResolution.y);
+        check(evplp_resolve(mHandle, vplScale, photonScale, lightScale, gamma ? 1 : 0, img.data()), "evplp_resolve");
+        return img;  // rows bottom-up, like glReadPixels
+    }
+
+    void pushParams(const Vec2& jitter, uint32_t rngSeed) {  // the rtContext[...]->set* block, :895-930, 873
+        EvplpParams P;
+        memset(&P, 0, sizeof(P));
+        const Vec3 o = mScene->mCamera->getOrigin();
+        P.cameraPosition[0] = o.x; P.cameraPosition[1] = o.y; P.cameraPosition[2] = o.z;
+        P.camForward[0] = mCamF.x; P.camForward[1] = mCamF.y; P.camForward[2] = mCamF.z;
+        P.camRight[0] = mCamS.x; P.camRight[1] = mCamS.y; P.camRight[2] = mCamS.z;
+        P.camUp[0] = mCamU.x; P.camUp[1] = mCamU.y; P.camUp[2] = mCamU.z;
+        P.tanHalfFovX = mTanHalfX; P.tanHalfFovY = mTanHalfY;
+        P.jitter[0] = jitter.x; P.jitter[1] = jitter.y;
+        P.nearDist = 0.1f; P.farDist = 100.0f;
+        P.numLightPaths = mNumLightPaths; P.numVplLightPaths = mNumVplLightPaths; P.numPhotonsPerLightPath = mNumPhotonsPerLightPath;
+        P.radius = mPhotonRadius; P.pdfMc = mPrecomptedPdfMc; P.misMode = (uint32_t)mMisMode; P.clampingValue = mClampingValue;
+        P.doAccumulate = mFrameMode == ClearEveryFrame ? 0u : 1u;
+        P.vslRadius = mVslRadius; P.vslInvPiRadius2 = mVslInvPiRadius2;
+        P.rngSeed = rngSeed;
+        check(evplp_set_params(mHandle, &P), "evplp_set_params");
+    }
+
+    // One pass of the loop body (rtcomphoton.h:936-1068).  Returns false when the loop must stop.
+    bool iterate() {
+        if (mNumIterations == mNumMaxIteration) return false;
+        Vec2 jitter;
+        if (mJitter) {
+            Vec2 xi = mMainSampler->nextVec2();
+            jitter.x = (2.0f * xi.x - 1.0f) * mInvResolution.x;
+            jitter.y = (2.0f * xi.y - 1.0f) * mInvResolution.y;
+        }
+        const bool mine = (mNumIterations % mWorldSize) == mRank;  // iteration partition over GPUs
+        if (mine) {
+            pushParams(jitter, (uint32_t)mNumIterations + mRngOffset);
+            if (mFrameMode == ClearEveryFrame) check(evplp_clear_accum(mHandle), "evplp_clear_accum");
+            if (mDoDeferredShading) runDeferredProgram();
+            if (mDoLightTracing) runOptixLightTracingProgram((uint32_t)mNumIterations + mRngOffset);
+            if (mDoVplSplat) runOptixVplProgram();
+            if (mDoPhotonSplat) runPhotonSplat();
+            if (mDoLightRender) runLightProgram();
+        }
+        mNumIterations++;
+        if (mNumIterations % 20 == 0 && mRank == 0) {
+            float currentTiming = mMasterWatch.timeMilliSec();
+            std::cout << "numIter: " << mNumIterations << " | raduis: " << mPhotonRadius << " | clamping: " << mClampingValue
+                      << " | timing: " << currentTiming - mPrevTiming << "\n";
+            mPrevTiming = currentTiming;
+        }
+        if (mDoProgressive) {  // :1033-1063 (types as in the reference: float ratio, double pow, float product)
+            float ratio = (mNumIterations + mAlphaProgressive) / (mNumIterations + 1);
+            mPhotonRadius *= std::sqrt(ratio);
+            mClampingValue = (float)(mClampingStart * std::pow((double)mNumIterations, (double)mAlphaProgressive));
+            mPrecomptedPdfMc = static_cast<float>(mNumVplLightPaths) / static_cast<float>(mNumLightPaths) * Math::InvPi / (mPhotonRadius * mPhotonRadius);
+            if (mForceVsl) {
+                mVslRadius *= std::sqrt(ratio);
+                if (mVslRadius <= 0.008f) mVslRadius = std::max(mVslRadius, 0.008f);
+                mVslInvPiRadius2 = Math::InvPi / (mVslRadius * mVslRadius);
+            }
+        }
+        if (mTimelimitMs > 0 && mMasterWatch.timeMilliSec() >= mTimelimitMs) return false;
+        return true;
+    }
+
+    // rtcomphoton.h:883-1133 (headless: RealTime::loop without the window)
+    void run() {
+        while (iterate()) {
+            if (mDoWriteEveryFrame && mWorldSize == 1) writeFrame();
+        }
+        finish();
+    }
+
+    void reduce() {
+        if (mWorldSize > 1 && mNcclComm) check(evplp_reduce(mHandle, mNcclComm), "evplp_reduce");
+    }
+
+    // the output block (:1107-1132)
+    void finish() {
+        reduce();
+        check(evplp_synchronize(mHandle), "evplp_synchronize");
+        const float time = mMasterWatch.timeMilliSec();
+        mElapsedMs = time;
+        if (mRank != 0 || !mWriteOutputs) return;
+        if (mUseStat) {
+            Json result = Json::make_object();
+            result.set("time", (double)time);
+            result.set("numIterations", (double)mNumIterations);
+            std::ofstream of(mStatFilename);
+            of << result.dump(4);
+        }
+        const float param = (mFrameMode == ClearEveryFrame) ? 1.0f : (1.0f / (float)(mNumIterations));
+        FloatImage lightSourceImage = FloatImage::FlipY(runFinalProgram(0.0f, 0.0f, 1.0f, false));
+        FloatImage photonImage = FloatImage::FlipY(runFinalProgram(0.0f, 1.0f, 0.0f, false));
+        photonImage *= param;
+        FloatImage vplImage = FloatImage::FlipY(runFinalProgram(1.0f, 0.0f, 0.0f, false));
+        vplImage *= param;
+        mCombined = lightSourceImage + vplImage + photonImage;
+        FloatImage::Save(mCombined, mDumpCombineFilename);
+        FloatImage::Save(lightSourceImage + vplImage, mDumpWeightedVplFilename);
+        FloatImage::Save(photonImage, mDumpWeightedPhotonFilename);
+    }
+
+    void writeFrame() {  // writeEveryFrame (:1079-1102)
+        const float param = (mFrameMode == ClearEveryFrame) ? 1.0f : (1.0f / (float)(mNumIterations));
+        FloatImage light = runFinalProgram(0.0f, 0.0f, 1.0f, false);
+        FloatImage photon = runFinalProgram(0.0f, 1.0f, 0.0f, false);
+        photon *= param;
+        FloatImage vpl = runFinalProgram(1.0f, 0.0f, 0.0f, false);
+        vpl *= param;
+        FloatImage result = light + photon + vpl;
+        size_t i = mDumpWeightedPhotonFilename.find_last_of('.');
+        std::string dotExtension = mDumpWeightedPhotonFilename.substr(i);
+        FloatImage::Save(FloatImage::FlipY(result), mDumpWeightedPhotonFilename.substr(0, i) + "_" + std::to_string(mNumIterations) + dotExtension);
+    }
+
+    void destroy() {  // :1135-1138
+        if (mHandle) { evplp_destroy(mHandle); mHandle = nullptr; }
+    }
+
+    evplp_handle handle() const { return mHandle; }
+    int numIterations() const { return mNumIterations; }
+    float elapsedMs() const { return mElapsedMs; }
+    const FloatImage& combined() const { return mCombined; }
+
+    // public like the reference's members so that callers (tests, bench) can override them
+    uint32_t mNumLightPaths = 0, mNumVplLightPaths = 0, mNumMaxBounce = 0, mNumPhotonsPerLightPath = 0, mRngOffset = 0;
+    float mRadiusPercentage = 0, mPhotonRadius = 0, mPrecomptedPdfMc = 0, mClampingValue = 0, mClampingStart = 0;
+    float mTimelimitMs = 0, mTargetRenderingTime = -1, mAlphaProgressive = 0.7f;
+    float mVslRadiusPercentage = 0, mVslRadius = 0, mVslInvPiRadius2 = 0;
+    int mNumMaxIteration = -1;
+    EFrame mFrameMode = Accumulate;
+    EMis mMisMode = Balance;
+    bool mJitter = true, mUseStat = false, mDoProgressive = false, mForceVsl = false, mDoWriteEveryFrame = false;
+    bool mDoDeferredShading = true, mDoLightTracing = true, mDoVplSplat = true, mDoPhotonSplat = true, mDoLightRender = true, mDoFinalize = true;
+    std::string mDumpCombineFilename, mDumpWeightedPhotonFilename, mDumpWeightedVplFilename, mStatFilename;
+
+protected:
+    void check(int rc, const char* what) {
+        if (rc != EVPLP_OK) throw std::runtime_error(std::string(what) + ": " + evplp_last_error());
+    }
+    int mDevice = 0, mBaseGatherMode = EVPLP_GATHER_VPL, mRank = 0, mWorldSize = 1;
+    void* mNcclComm = nullptr;
+    bool mWriteOutputs = true;
+    evplp_handle mHandle = nullptr;
+    shared_ptr<RtScene> mScene;
+    Vec2 mResolution, mInvResolution;
+    Vec3 mCamF, mCamS, mCamU;
+    float mTanHalfX = 0, mTanHalfY = 0;
+    std::unique_ptr<IndependentSampler> mMainSampler;
+    int mNumIterations = 0;
+    StopWatch mMasterWatch;
+    float mPrevTiming = 0, mElapsedMs = 0;
+    FloatImage mCombined;
+};
+
+// RtLvcComPhoton (rtlvccomphoton.h + lvclighttracing.cu:348-387): the same technique whose gather
+// picks, per pixel, a random window of numVplLightPaths paths out of all numLightPaths.
+class RtLvcComPhoton : public RtComPhoton {
+public:
+    explicit RtLvcComPhoton(int device = 0) : RtComPhoton(device, EVPLP_GATHER_LVC) {}
+};
+
+}  // namespace evplp_host

@@ -1,0 +1,197 @@
+"""ctypes view of libevplp_host.so: the C++ host classes (RtScene, RtComPhoton, scene
+generator) of evplp_b200/host/.  Scene data preparation only; rendering goes through
+libevplp_b200.so."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import _capi as capi
+from .scene import Material, Mesh, Scene
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "lib", "libevplp_host.so")
+_P = C.c_void_p
+_lib = None
+
+
+def load_host_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    capi.load_library()  # libevplp_b200.so first (RTLD_GLOBAL)
+    if not os.path.exists(HOST_LIB_PATH):
+        raise RuntimeError(f"{HOST_LIB_PATH} not found: run __graft_entry__.build()")
+    lib = C.CDLL(HOST_LIB_PATH)
+    lib.evplp_host_last_error.restype = C.c_char_p
+    lib.evplp_host_export_scene.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    lib.evplp_host_generate_scene.restype = _P
+    lib.evplp_host_generate_scene.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_float]
+    lib.evplp_host_load_scene.restype = _P
+    lib.evplp_host_load_scene.argtypes = [C.c_char_p]
+    lib.evplp_host_scene_destroy.argtypes = [_P]
+    lib.evplp_host_scene_descriptors.argtypes = [_P, C.POINTER(C.POINTER(capi.MeshDesc)), C.POINTER(C.c_int32),
+                                                 C.POINTER(C.POINTER(capi.MaterialDesc)), C.POINTER(C.c_int32),
+                                                 C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.evplp_host_scene_info.argtypes = [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.evplp_host_technique_create.restype = _P
+    lib.evplp_host_technique_create.argtypes = [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.evplp_host_technique_handle.restype = _P
+    lib.evplp_host_technique_handle.argtypes = [_P]
+    lib.evplp_host_technique_iterate.argtypes = [_P]
+    lib.evplp_host_technique_state.argtypes = [_P, C.POINTER(C.c_float)]
+    lib.evplp_host_technique_final.argtypes = [_P, C.c_float, C.c_float, C.c_float, C.c_int, _P]
+    lib.evplp_host_technique_destroy.argtypes = [_P]
+    lib.evplp_host_render_json.argtypes = [C.c_char_p, C.c_int]
+    lib.evplp_host_pfm_relmse.restype = C.c_float
+    lib.evplp_host_pfm_relmse.argtypes = [C.c_char_p, C.c_char_p]
+    _lib = lib
+    return lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _err(lib, what):
+    raise HostError(f"{what}: {lib.evplp_host_last_error().decode()}")
+
+
+class HostScene:
+    """An RtScene living in the C++ host library."""
+
+    def __init__(self, handle):
+        self.lib = load_host_library()
+        self.h = handle
+        s = (C.c_float * 3)()
+        cam = (C.c_float * 14)()
+        if self.lib.evplp_host_scene_info(self.h, s, cam) != 0:
+            _err(self.lib, "evplp_host_scene_info")
+        self.bounding_sphere_radius = np.float32(s[0])
+        self.total_area = np.float32(s[1])
+        self.num_triangles = int(s[2])
+        c = np.array(list(cam), dtype=np.float32)
+        self.cam_origin, self.cam_forward, self.cam_right, self.cam_up = c[0:3], c[3:6], c[6:9], c[9:12]
+        self.tan_x, self.tan_y = c[12], c[13]
+
+    @classmethod
+    def generate(cls, name, seed=1, detail=8, aspect=16 / 9):
+        lib = load_host_library()
+        h = lib.evplp_host_generate_scene(name.encode(), seed, detail, aspect)
+        if not h:
+            _err(lib, "evplp_host_generate_scene")
+        return cls(h)
+
+    @classmethod
+    def load(cls, json_path):
+        lib = load_host_library()
+        h = lib.evplp_host_load_scene(json_path.encode())
+        if not h:
+            _err(lib, "evplp_host_load_scene")
+        return cls(h)
+
+    def close(self):
+        if self.h:
+            self.lib.evplp_host_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def to_scene(self):
+        """Copy into the numpy Scene container (what the oracle and Device.upload_scene take)."""
+        md = C.POINTER(capi.MeshDesc)(); mt = C.POINTER(capi.MaterialDesc)()
+        nm = C.c_int32(); nt = C.c_int32(); li = C.c_int32()
+        pre = (C.c_float * 4)(); disp = (C.c_float * 4)()
+        self.lib.evplp_host_scene_descriptors(self.h, C.byref(md), C.byref(nm), C.byref(mt), C.byref(nt), C.byref(li), pre, disp)
+        sc = Scene()
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(n,)).copy()
+
+        for k in range(nt.value):
+            m = mt[k]
+            mat = Material.__new__(Material)
+            mat.lambert = arr(m.lambertReflectance, m.lambertW * m.lambertH * 4, C.c_float).reshape(m.lambertH, m.lambertW, 4)
+            mat.phong = arr(m.phongReflectance, m.phongW * m.phongH * 4, C.c_float).reshape(m.phongH, m.phongW, 4)
+            mat.exponent = arr(m.phongExponent, m.exponentW * m.exponentH * 4, C.c_float).reshape(m.exponentH, m.exponentW, 4)
+            mat.lightIntensity = np.array(list(m.lightIntensity), dtype=np.float32)
+            sc.materials.append(mat)
+        for k in range(nm.value):
+            m = md[k]
+            v = arr(m.vertices, m.numVertices * 3, C.c_float)
+            t = arr(m.texcoords, m.numVertices * 2, C.c_float) if m.texcoords else None
+            i = arr(m.indices, m.numTriangles * 3, C.c_int32)
+            sc.meshes.append(Mesh(v, i, m.matIndex, t))
+        sc.light_mesh = li.value
+        sc.light_intensity = np.array(list(disp), dtype=np.float32)
+        return sc
+
+    def camera(self):
+        class _Cam:
+            pass
+
+        c = _Cam()
+        c.origin, c.forward, c.right, c.up, c.tan_x, c.tan_y = self.cam_origin, self.cam_forward, self.cam_right, self.cam_up, self.tan_x, self.tan_y
+        return c
+
+
+class Technique:
+    """RtComPhoton (or RtLvcComPhoton) of the C++ host library, stepped one iteration at a time."""
+
+    def __init__(self, host_scene, photonfam, res_x, res_y, device=0, lvc=False, rank=0, world_size=1):
+        self.lib = load_host_library()
+        self.W, self.H = res_x, res_y
+        text = json.dumps(photonfam).encode()
+        self.h = self.lib.evplp_host_technique_create(host_scene.h, text, res_x, res_y, device, 1 if lvc else 0, rank, world_size)
+        if not self.h:
+            _err(self.lib, "evplp_host_technique_create")
+        self._scene = host_scene
+
+    def device_handle(self):
+        return C.c_void_p(self.lib.evplp_host_technique_handle(self.h))
+
+    def iterate(self):
+        rc = self.lib.evplp_host_technique_iterate(self.h)
+        if rc < 0:
+            _err(self.lib, "evplp_host_technique_iterate")
+        return rc == 1
+
+    def state(self):
+        s = (C.c_float * 6)()
+        self.lib.evplp_host_technique_state(self.h, s)
+        return dict(radius=s[0], clamping=s[1], pdfMc=s[2], vslRadius=s[3], vslInvPiRadius2=s[4], numIterations=int(s[5]))
+
+    def final(self, vpl_scale, photon_scale, light_scale, gamma=False, out=None):
+        if out is None:
+            out = np.empty((self.H, self.W, 3), dtype=np.float32)
+        if self.lib.evplp_host_technique_final(self.h, vpl_scale, photon_scale, light_scale, 1 if gamma else 0, capi.ptr(out)) != 0:
+            _err(self.lib, "evplp_host_technique_final")
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.evplp_host_technique_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def export_scene(name, out_dir, seed=1, detail=8, res_x=1280, res_y=720):
+    lib = load_host_library()
+    if lib.evplp_host_export_scene(name.encode(), out_dir.encode(), seed, detail, res_x, res_y) != 0:
+        _err(lib, "evplp_host_export_scene")
+
+
+def render_json(json_path, device=0):
+    lib = load_host_library()
+    if lib.evplp_host_render_json(json_path.encode(), device) != 0:
+        _err(lib, "evplp_host_render_json")

@@ -247,9 +247,11 @@ static void splat_rect(const EvplpParams* P, int32_t W, int32_t H, const float* 
     double xv = c[0] * P->camRight[0] + c[1] * P->camRight[1] + c[2] * P->camRight[2];
     double yv = c[0] * P->camUp[0] + c[1] * P->camUp[1] + c[2] * P->camUp[2];
     double rr = (double)r * 1.001 + 1e-6;
-    *x0 = 0; *y0 = 0; *x1 = W; *y1 = H;
-    if (z - rr <= 1e-4) return;  // sphere reaches the camera plane: whole screen
-    double zn = z - rr, zf = z + rr;
+    // G-buffer points lie at depth >= nearDist along the forward axis (primary rays start at tmin = nearDist)
+    const double zNear = (double)P->nearDist * 0.999;
+    *x0 = 0; *y0 = 0; *x1 = 0; *y1 = 0;
+    if (z + rr < zNear) return;  // sphere entirely behind the near plane: no texel can be inside it
+    double zn = std::max(z - rr, zNear), zf = z + rr;
     auto range = [&](double v, double tanHalf, double jit, int N, int* lo, int* hi) {
         double a = (v - rr), b = (v + rr);
         double lo_ndc = std::min(a / zn, a / zf) / tanHalf + jit;
