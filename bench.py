@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- the EVPLP hot path on B200: one progressive iteration per step.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (the CPU restatement on the host cores)
+
+Workload (BASELINE.json configs[1]): procedural conference-like scene (334 k triangles,
+the real OBJ is a git-LFS pointer), 1920x1080, progressive VPL + photon splatting
+("ours_progressive": balance-heuristic MIS, radius 0.3 % shrinking by the Knaus-Zwicker
+schedule), numVplLightPaths = 16384 (64 k VPL record slots per iteration),
+numLightPaths = 300000 (the bundled value), 3 bounces, jitter on, rngOffset 0.
+
+A step = G-buffer -> light trace -> VPL gather -> photon splat -> light pass of ONE
+iteration, driven by the C++ RtComPhoton class through the C ABI.  With N GPUs the
+iterations are dealt round-robin (rank g renders k = g mod N), so per-GPU work is fixed
+("weak"); the accumulation layers are all-reduced (NCCL) once at the end of the timed batch.
+
+value  = VPL-pixel pairs / s over all ranks, device-timed (CUDA events on the stream the
+         kernels are launched on), inputs resident in HBM.
+e2e    = the same through the host-buffer path: every step also resolves the running image
+         and copies it to host memory (D2H), parameters + RNG skip matrix go H2D.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES_X, RES_Y = 1920, 1080
+SCENE, SEED, DETAIL = "conference", 1, 8
+PHOTONFAM = {
+    "rngOffset": 0, "numMaxIteration": -1, "timeLimitMs": -1.0, "frameMode": "accumulate", "renderMode": "vplpm",
+    "combinedFilename": "bench_combined.pfm", "weightedPhotonFilename": "bench_weightedpm.pfm",
+    "weightedVplFilename": "bench_weightedvpl.pfm", "statFilename": "bench_stat.json", "useJitter": True, "useStat": False,
+    "numLightPaths": 300000, "numVplLightPaths": 16384, "numMaxBounces": 3, "radiusPercentage": 0.003,
+    "DoProgressive": True, "AlphaProgressive": 0.7,
+}
+FLOP_PER_PAIR = 300.0  # misMode 1-3 (balance) = ~300 FP32 flop per (pixel, VPL) pair
+WORKLOAD = ("conference-like procedural scene 334k tris, 1920x1080, progressive VPL gather + photon splat, "
+            "numVplLightPaths=16384 (64k VPL slots/iter), numLightPaths=300000, 3 bounces, balance MIS")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference's device programs) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_sample(steps, warmup, tile_w=32, tile_h=16):
+    """Times the oracle on a BOUNDED sample of the workload: the full VPL set of one iteration
+    gathered into a tile_w x tile_h pixel tile at the image centre (pairs/s does not depend on
+    the tile size).  Returns (pairs_per_s, seconds_per_step, cores, description)."""
+    from evplp_b200 import host_api as HA, _capi as capi, scene as S
+    from tests import oracle_api as O
+
+    hs = HA.HostScene.generate(SCENE, SEED, DETAIL, RES_X / RES_Y)
+    sc = hs.to_scene()
+    orc = O.OracleScene(sc)
+    cores = O.load().orc_num_threads()
+    cam = hs.camera()
+    nvpl, npaths = PHOTONFAM["numVplLightPaths"], PHOTONFAM["numLightPaths"]
+    radius = float(hs.bounding_sphere_radius) * PHOTONFAM["radiusPercentage"]
+    P = S.make_params(cam, npaths, nvpl, 3, radius, mis_mode=capi.MIS_BALANCE, clamp=float(1.0 / hs.total_area), rng_seed=0)
+    x0, y0 = RES_X // 2 - tile_w // 2, RES_Y // 2 - tile_h // 2
+    tile = (x0, y0, x0 + tile_w, y0 + tile_h)
+    # G-buffer of the tile only (the oracle gathers from full-size planes; fill just the tile rows/cols)
+    planes = np.zeros((4, RES_Y, RES_X, 4), dtype=np.float32)
+    prims = np.full((RES_Y, RES_X), -1, dtype=np.int32)
+    # trace only the VPL prefix (the gather reads nothing else)
+    rec = orc.light_trace(P, 0, 0, nvpl)
+    # primary rays of the tile through the oracle's generic ray tap
+    gp, gprim = _oracle_gbuffer_tile(orc, P, tile)
+    planes[:, y0:y0 + tile_h, x0:x0 + tile_w, :] = gp
+    prims[y0:y0 + tile_h, x0:x0 + tile_w] = gprim
+    times, pairs = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, cnt = orc.vpl_gather(P, RES_X, RES_Y, planes, prims, rec, capi.GATHER_VPL, tile=tile)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt); pairs = int(cnt[0])
+    sec = float(np.mean(times))
+    desc = (f"oracle VPL gather of one iteration's full VPL set ({pairs // (tile_w * tile_h)} usable VPLs) into a "
+            f"{tile_w}x{tile_h} px centre tile = {pairs} pairs per step, {cores} OpenMP threads")
+    return pairs / sec, sec, cores, desc
+
+
+def _oracle_gbuffer_tile(orc, P, tile):
+    """G-buffer texels of a tile via a full-res oracle call restricted by a cheap trick: the oracle's
+    orc_gbuffer renders W x H, so render a temporary image of exactly the tile by shifting NDC."""
+    # Simple and exact: call the full G-buffer routine on the tile's rows only would need a new entry point;
+    # instead evaluate the whole image lazily at low cost: 1080p G-buffer on the oracle takes a few seconds.
+    planes, prims = orc.gbuffer(P, RES_X, RES_Y)
+    x0, y0, x1, y1 = tile
+    return planes[:, y0:y1, x0:x1, :], prims[y0:y1, x0:x1]
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    pps, sec, cores, desc = cpu_sample(args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "VPL-pixel pairs/s", "value": pps, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "the reference (VS2015 + CUDA 8 + OptiX 4.1.1 + OpenGL) cannot be built or run "
+                   "here; this arm times the scalar C++ restatement of its device programs (oracle/) on the host cores"},
+        "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from evplp_b200 import host_api as HA, _capi as capi
+
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    lib = capi.load_library()
+
+    hs = HA.HostScene.generate(SCENE, SEED, DETAIL, RES_X / RES_Y)
+    tech = HA.Technique(hs, PHOTONFAM, RES_X, RES_Y, device=local_rank, rank=rank, world_size=world)
+    h = tech.device_handle()
+
+    def ck(rc, what):
+        capi.check(lib, rc, what)
+
+    def barrier():
+        ck(lib.evplp_synchronize(h), "sync")
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def all_reduce_layers():
+        if world == 1:
+            return
+        ck(lib.evplp_synchronize(h), "sync")
+        for layer, typestr in ((0, "<i8"), (1, "<i8"), (2, "<i4")):
+            p, n = C.c_void_p(), C.c_uint64()
+            ck(lib.evplp_accum_layer(h, layer, C.byref(p), C.byref(n)), "accum_layer")
+
+            class _W:
+                __cuda_array_interface__ = {"shape": (n.value,), "typestr": typestr, "data": (p.value, False), "version": 2}
+
+            t = torch.as_tensor(_W(), device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+
+    def step():
+        # one iteration of THIS rank: advance the global loop until an iteration of ours has run
+        for _ in range(world):
+            tech.iterate()
+
+    def stats():
+        s = capi.Stats()
+        ck(lib.evplp_stats(h, C.byref(s)), "stats")
+        return s
+
+    def launches():
+        n = C.c_uint64()
+        ck(lib.evplp_launch_count(h, C.byref(n)), "launch_count")
+        return n.value
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region 1: device-timed, inputs resident
+    ck(lib.evplp_reset_stats(h), "reset_stats")
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = launches()
+    barrier()
+    t0 = time.perf_counter()
+    ck(lib.evplp_event_record(h, 0), "event")
+    stage_ms = np.zeros(4)
+    for _ in range(args.steps):
+        step()
+        for k, st in enumerate((capi.STAGE_GBUFFER, capi.STAGE_LIGHT_TRACE, capi.STAGE_GATHER, capi.STAGE_SPLAT)):
+            ms = C.c_float()
+            ck(lib.evplp_last_stage_ms(h, st, C.byref(ms)), "stage_ms")
+            stage_ms[k] += ms.value
+    all_reduce_layers()
+    ck(lib.evplp_event_record(h, 1), "event")
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = C.c_float()
+    ck(lib.evplp_event_elapsed_ms(h, 0, 1, C.byref(ms)), "elapsed")
+    l1 = launches()
+    clk = clocks.stop()
+    st = stats()
+    dev_s = max(ms.value / 1e3, 1e-9)
+    # the all-reduce runs on torch's stream after our stream was synchronised: count it via wall clock when N > 1
+    sec = max(dev_s, wall) if world > 1 else dev_s
+    mine = torch.tensor([sec, float(st.gatherPairs), float(st.splatPhotons), float(st.splatFragments), float(st.shadowRays)],
+                        dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        tmax = mine.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = mine.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        sec = float(tmax[0]); pairs, photons, frags, rays = (float(x) for x in tsum[1:])
+    else:
+        pairs, photons, frags, rays = (float(x) for x in mine[1:])
+
+    # ---- timed region 2: end to end through host buffers (resolve + D2H every step)
+    out = np.empty((RES_Y, RES_X, 3), dtype=np.float32)
+    barrier()
+    ck(lib.evplp_reset_stats(h), "reset_stats")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        n_it = tech.state()["numIterations"]
+        tech.final(1.0 / n_it, 1.0 / n_it, 1.0, gamma=True, out=out)
+    barrier()
+    e2e_sec = time.perf_counter() - t0
+    st2 = stats()
+    e2e = torch.tensor([e2e_sec, float(st2.gatherPairs)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        m = e2e.clone(); dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        s = e2e.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        e2e_sec, e2e_pairs = float(m[0]), float(s[1])
+    else:
+        e2e_pairs = float(e2e[1])
+
+    if rank == 0:
+        hbm, sm_max, how = peaks()
+        gather_s = stage_ms[2] / 1e3
+        splat_s = max(stage_ms[3] / 1e3, 1e-9)
+        my_pairs, my_photons = float(st.gatherPairs), float(st.splatPhotons)
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s
+        ach = my_pairs * FLOP_PER_PAIR / max(gather_s, 1e-9) / 1e12
+        nrec = PHOTONFAM["numLightPaths"] * 4
+        splat_bytes = (96.0 * nrec + 64.0 * RES_X * RES_Y + 48.0 * RES_X * RES_Y) * args.steps
+        line = {
+            "metric": "VPL-pixel pairs/s", "value": pairs / sec, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "partition": f"iterations round-robin over {world} GPU(s), one all-reduce of the "
+                       "int64 accumulation layers per timed batch", "l2": "inputs larger than L2: per iteration 133 MB G-buffer + "
+                       "115 MB records + 100 MB accumulators are rewritten/re-read"},
+            "splatted_photons_per_s": photons / sec, "splat_fragments_per_s": frags / sec, "shadow_rays_per_s": rays / sec,
+            "ms_per_iteration": sec * 1e3 / args.steps,
+            "stage_ms_per_step_rank0": {"gbuffer": stage_ms[0] / args.steps, "light_trace": stage_ms[1] / args.steps,
+                                        "vpl_gather": stage_ms[2] / args.steps, "photon_splat": stage_ms[3] / args.steps},
+            "roofline": {"kernel": "gather_vpl_kernel", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": ach / fp32_peak, "traffic": None,
+                         "note": f"{FLOP_PER_PAIR:.0f} algorithmic FP32 flop per pair (SURVEY 8d) x pairs / gather kernel time; peak = "
+                                 f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz ({how} clock); the kernel is shadow-ray traversal bound, "
+                                 "not HBM or tensor bound"},
+            "roofline_splat": {"kernel": "splat_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
+                               "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": None,
+                               "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}"},
+            "clocks": clk, "gpu_launches": int(l1 - l0),
+            "e2e": {"value": e2e_pairs / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 3200 + C.sizeof(capi.Params),
+                    "d2h_bytes_per_step": RES_X * RES_Y * 12 + 16},
+        }
+        if world == 1 and not args.no_cpu:
+            pps, csec, cores, desc = cpu_sample(1, 0)
+            line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line))
+    tech.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="evplp_b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    # profiling aids only (ncu replays every kernel ~40 times): the headline workload is the default
+    ap.add_argument("--vpl-paths", type=int, default=None, help="override numVplLightPaths (profiling only)")
+    ap.add_argument("--light-paths", type=int, default=None, help="override numLightPaths (profiling only)")
+    ap.add_argument("--res", default=None, help="override WxH (profiling only)")
+    args = ap.parse_args()
+    global RES_X, RES_Y, WORKLOAD
+    if args.vpl_paths is not None:
+        PHOTONFAM["numVplLightPaths"] = args.vpl_paths
+    if args.light_paths is not None:
+        PHOTONFAM["numLightPaths"] = args.light_paths
+    if args.res:
+        RES_X, RES_Y = (int(v) for v in args.res.lower().split("x"))
+    if args.vpl_paths is not None or args.light_paths is not None or args.res:
+        WORKLOAD = (f"NON-HEADLINE profiling override: {RES_X}x{RES_Y}, numVplLightPaths={PHOTONFAM['numVplLightPaths']}, "
+                    f"numLightPaths={PHOTONFAM['numLightPaths']}; " + WORKLOAD)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,24 +31,6 @@ DevScene EvplpContext::scene() const {
     return s;
 }
 
-namespace {
-struct StageTimer {
-    EvplpContext* c;
-    int stage;
-    StageTimer(EvplpContext* c_, int s) : c(c_), stage(s) { cudaEventRecord(c->evA, c->stream); }
-    void stop() { cudaEventRecord(c->evB, c->stream); c->stageMs[stage] = -1.f; pending = true; }
-    bool pending = false;
-};
-}  // namespace
-
-// stage times are resolved lazily (evplp_last_stage_ms synchronizes) so that stages stay asynchronous;
-// each stage owns an event pair.
-struct StageEvents {
-    cudaEvent_t a[ST_COUNT], b[ST_COUNT];
-    bool valid[ST_COUNT];
-};
-static StageEvents* events_of(EvplpContext* c);
-
 extern "C" {
 
 const char* evplp_last_error(void) { return g_err.c_str(); }
@@ -61,27 +43,6 @@ int evplp_device_count(void) {
 }
 
 }  // extern "C"
-
-struct CtxExtra {
-    StageEvents ev;
-};
-static std::vector<std::pair<EvplpContext*, CtxExtra*>> g_extras;
-static StageEvents* events_of(EvplpContext* c) {
-    for (auto& p : g_extras) if (p.first == c) return &p.second->ev;
-    return nullptr;
-}
-
-static int begin_stage(EvplpContext* c, int s) {
-    StageEvents* e = events_of(c);
-    cudaEventRecord(e->a[s], c->stream);
-    return 0;
-}
-static int end_stage(EvplpContext* c, int s) {
-    StageEvents* e = events_of(c);
-    cudaEventRecord(e->b[s], c->stream);
-    e->valid[s] = true;
-    return 0;
-}
 
 static int check_overflow(EvplpContext* c) {
     DevStats ds;
@@ -109,15 +70,11 @@ int evplp_create(int device, int width, int height, evplp_handle* out) {
     EvplpContext* c = new EvplpContext();
     c->device = device; c->W = width; c->H = height;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&c->evA));
-    CU(cudaEventCreate(&c->evB));
-    CtxExtra* ex = new CtxExtra();
     for (int s = 0; s < ST_COUNT; s++) {
-        CU(cudaEventCreate(&ex->ev.a[s]));
-        CU(cudaEventCreate(&ex->ev.b[s]));
-        ex->ev.valid[s] = false;
+        CU(cudaEventCreate(&c->stageA[s]));
+        CU(cudaEventCreate(&c->stageB[s]));
     }
-    g_extras.push_back({c, ex});
+    for (int s = 0; s < 4; s++) CU(cudaEventCreate(&c->userEv[s]));
     const size_t n_px = (size_t)width * height;
     CU(c->gbuf.reserve(4 * n_px));
     CU(c->gprim.reserve(n_px));
@@ -155,15 +112,8 @@ int evplp_destroy(evplp_handle c) {
     c->vplList.release(); c->photonList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
     c->accPhoton.release(); c->accLight.release(); c->resolveOut.release(); c->devStats.release();
     if (c->resolvePinned) cudaFreeHost(c->resolvePinned);
-    for (size_t i = 0; i < g_extras.size(); i++) {
-        if (g_extras[i].first == c) {
-            for (int s = 0; s < ST_COUNT; s++) { cudaEventDestroy(g_extras[i].second->ev.a[s]); cudaEventDestroy(g_extras[i].second->ev.b[s]); }
-            delete g_extras[i].second;
-            g_extras.erase(g_extras.begin() + i);
-            break;
-        }
-    }
-    cudaEventDestroy(c->evA); cudaEventDestroy(c->evB);
+    for (int s = 0; s < ST_COUNT; s++) { cudaEventDestroy(c->stageA[s]); cudaEventDestroy(c->stageB[s]); }
+    for (int s = 0; s < 4; s++) cudaEventDestroy(c->userEv[s]);
     cudaStreamDestroy(c->stream);
     delete c;
     return EVPLP_OK;
@@ -259,10 +209,10 @@ int evplp_build_bvh(evplp_handle c) {
     NEED(c != nullptr, "evplp_build_bvh: NULL handle");
     NEED(c->sceneLoaded, "evplp_build_bvh: no scene uploaded");
     CU(cudaSetDevice(c->device));
-    begin_stage(c, ST_BVH);
+    c->stageBegin(ST_BVH);
     std::string err;
     cudaError_t e = build_bvh_device(c, &err);
-    end_stage(c, ST_BVH);
+    c->stageEnd(ST_BVH);
     if (e != cudaSuccess) return fail(EVPLP_ERR_CUDA, "evplp_build_bvh: " + err);
     CU(cudaStreamSynchronize(c->stream));
     return EVPLP_OK;
@@ -303,9 +253,7 @@ int evplp_gbuffer(evplp_handle c) {
     NEED(c != nullptr, "evplp_gbuffer: NULL handle");
     NEED(c->bvhBuilt && c->paramsSet, "evplp_gbuffer: needs evplp_build_bvh and evplp_set_params first");
     CU(cudaSetDevice(c->device));
-    begin_stage(c, ST_GBUFFER);
     CU(launch_gbuffer(c));
-    end_stage(c, ST_GBUFFER);
     c->gbufValid = true;
     return EVPLP_OK;
 }
@@ -319,9 +267,7 @@ int evplp_light_trace(evplp_handle c, uint32_t rngSeed, uint32_t firstPath, uint
     CU(c->records.reserve(nrec));
     int rc = ensure_skip_matrix(c, rngSeed);
     if (rc) return rc;
-    begin_stage(c, ST_LIGHT_TRACE);
     CU(launch_light_trace(c, rngSeed, firstPath, numPaths));
-    end_stage(c, ST_LIGHT_TRACE);
     c->numRecords = nrec;
     c->recordsFirstPath = firstPath;
     return EVPLP_OK;
@@ -348,9 +294,7 @@ int evplp_vpl_gather(evplp_handle c, const EvplpTile* tile, int gatherMode) {
     int rc = tile_of(c, tile, &t);
     if (rc) return rc;
     if (gatherMode != EVPLP_GATHER_VPL) { rc = ensure_skip_matrix(c, c->params.rngSeed); if (rc) return rc; }
-    begin_stage(c, ST_GATHER);
     CU(launch_gather(c, t, gatherMode));
-    end_stage(c, ST_GATHER);
     return EVPLP_OK;
 }
 
@@ -362,9 +306,7 @@ int evplp_photon_splat(evplp_handle c, uint64_t firstRecord, uint64_t numRecords
     EvplpTile t;
     int rc = tile_of(c, tile, &t);
     if (rc) return rc;
-    begin_stage(c, ST_SPLAT);
     CU(launch_splat(c, firstRecord, numRecords, t));
-    end_stage(c, ST_SPLAT);
     return EVPLP_OK;
 }
 
@@ -419,9 +361,7 @@ int evplp_accum_layer(evplp_handle c, int layer, void** devPtr, uint64_t* numEle
 int evplp_resolve(evplp_handle c, float vplScale, float photonScale, float lightScale, int doGammaCorrection, float* hostRGB) {
     NEED(c != nullptr && hostRGB != nullptr, "evplp_resolve: NULL argument");
     CU(cudaSetDevice(c->device));
-    begin_stage(c, ST_RESOLVE);
     CU(launch_resolve(c, vplScale, photonScale, lightScale, doGammaCorrection));
-    end_stage(c, ST_RESOLVE);
     const size_t bytes = sizeof(float) * 3 * (size_t)c->W * c->H;
     CU(cudaMemcpyAsync(c->resolvePinned, c->resolveOut.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -612,11 +552,10 @@ int evplp_reset_stats(evplp_handle c) {
 int evplp_last_stage_ms(evplp_handle c, int stage, float* ms) {
     NEED(c != nullptr && ms != nullptr, "evplp_last_stage_ms: NULL argument");
     NEED(stage >= 0 && stage < ST_COUNT, "evplp_last_stage_ms: stage out of range");
-    StageEvents* e = events_of(c);
-    NEED(e && e->valid[stage], "evplp_last_stage_ms: the stage has not run yet");
+    NEED(c->stageValid[stage], "evplp_last_stage_ms: the stage has not run yet");
     CU(cudaSetDevice(c->device));
-    CU(cudaEventSynchronize(e->b[stage]));
-    CU(cudaEventElapsedTime(ms, e->a[stage], e->b[stage]));
+    CU(cudaEventSynchronize(c->stageB[stage]));
+    CU(cudaEventElapsedTime(ms, c->stageA[stage], c->stageB[stage]));
     return EVPLP_OK;
 }
 
@@ -630,6 +569,21 @@ int evplp_synchronize(evplp_handle c) {
 int evplp_launch_count(evplp_handle c, uint64_t* count) {
     NEED(c != nullptr && count != nullptr, "evplp_launch_count: NULL argument");
     *count = c->launches;
+    return EVPLP_OK;
+}
+
+int evplp_event_record(evplp_handle c, int slot) {
+    NEED(c != nullptr && slot >= 0 && slot < 4, "evplp_event_record: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->userEv[slot], c->stream));
+    return EVPLP_OK;
+}
+
+int evplp_event_elapsed_ms(evplp_handle c, int slotA, int slotB, float* ms) {
+    NEED(c != nullptr && ms && slotA >= 0 && slotA < 4 && slotB >= 0 && slotB < 4, "evplp_event_elapsed_ms: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->userEv[slotB]));
+    CU(cudaEventElapsedTime(ms, c->userEv[slotA], c->userEv[slotB]));
     return EVPLP_OK;
 }
 

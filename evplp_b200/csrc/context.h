@@ -40,8 +40,11 @@ struct EvplpContext {
     int device = 0;
     int W = 0, H = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t evA = nullptr, evB = nullptr;
-    float stageMs[evplp::ST_COUNT] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t stageA[evplp::ST_COUNT] = {}, stageB[evplp::ST_COUNT] = {};  // device time of each stage's main kernel(s)
+    bool stageValid[evplp::ST_COUNT] = {};
+    cudaEvent_t userEv[4] = {};                                              // evplp_event_record slots
+    void stageBegin(int s) { cudaEventRecord(stageA[s], stream); }
+    void stageEnd(int s) { cudaEventRecord(stageB[s], stream); stageValid[s] = true; }
     uint64_t launches = 0;
 
     // scene

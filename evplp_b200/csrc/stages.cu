@@ -670,7 +670,9 @@ static cudaError_t compact_records(EvplpContext* c, uint64_t first, uint64_t cou
 // ------------------------------------------------------------------ launchers -----------
 cudaError_t launch_gbuffer(EvplpContext* c) {
     dim3 grid((c->W + 15) / 16, (c->H + 7) / 8);
+    c->stageBegin(ST_GBUFFER);
     gbuffer_kernel<<<grid, 128, 0, c->stream>>>(c->scene(), cam_of(c->params), c->W, c->H, c->gbuf.p, c->gprim.p, c->devStats.p);
+    c->stageEnd(ST_GBUFFER);
     c->launches++;
     c->stats.closestRays += (uint64_t)c->W * c->H;
     return cudaGetLastError();
@@ -680,8 +682,10 @@ cudaError_t launch_light_trace(EvplpContext* c, uint32_t rngSeed, uint32_t first
     (void)rngSeed;
     if (numPaths == 0) return cudaSuccess;
     const uint32_t B1 = c->params.numPhotonsPerLightPath;
+    c->stageBegin(ST_LIGHT_TRACE);
     light_trace_kernel<<<(numPaths + 127) / 128, 128, 0, c->stream>>>(c->scene(), c->skipMatrix.p, c->records.p, firstPath,
                                                                       numPaths, B1, c->devStats.p);
+    c->stageEnd(ST_LIGHT_TRACE);
     c->launches++;
     return cudaGetLastError();
 }
@@ -710,8 +714,10 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     dim3 grid((tw + 15) / 16, (th + 15) / 16, 1);
     cudaError_t e;
     if (mode == EVPLP_GATHER_LVC) {
+        c->stageBegin(ST_GATHER);
         gather_lvc_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->skipMatrix.p, c->gbuf.p, c->records.p,
                                                                       c->accVpl.p, c->devStats.p);
+        c->stageEnd(ST_GATHER);
         c->launches++;
         return cudaGetLastError();
     }
@@ -727,8 +733,10 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     if (e != cudaSuccess) return e;
     c->stats.gatherPairs += (uint64_t)count * (uint64_t)tw * th;
     if (mode == EVPLP_GATHER_VSL) {
+        c->stageBegin(ST_GATHER);
         gather_vsl_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->skipMatrix.p, c->gbuf.p, c->records.p,
                                                                       c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+        c->stageEnd(ST_GATHER);
         c->launches++;
         return cudaGetLastError();
     }
@@ -750,8 +758,10 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         clear_tile_kernel<<<cg, 128, 0, c->stream>>>(c->accVpl.p, c->W, t.x0, t.y0, t.x1, t.y1);
         c->launches++;
     }
+    c->stageBegin(ST_GATHER);
     gather_vpl_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount,
                                                                   c->accVpl.p, c->devStats.p);
+    c->stageEnd(ST_GATHER);
     c->launches++;
     return cudaGetLastError();
 }
@@ -780,8 +790,10 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
     uint32_t blocks = (warpsWanted + 7) / 8;
     const uint32_t maxBlocks = 148u * 8u * 4u;
     if (blocks > maxBlocks) blocks = maxBlocks;
+    c->stageBegin(ST_SPLAT);
     splat_kernel<<<blocks, 256, 0, c->stream>>>(sp, c->gbuf.p, c->gprim.p, c->records.p, c->photonList.p, devCount,
                                                 c->accPhoton.p, c->devStats.p);
+    c->stageEnd(ST_SPLAT);
     c->launches++;
     return cudaGetLastError();
 }
@@ -798,7 +810,9 @@ cudaError_t launch_resolve(EvplpContext* c, float vplScale, float photonScale, f
     ResolveParams rp;
     rp.vplScale = vplScale; rp.photonScale = photonScale; rp.lightScale = lightScale; rp.gamma = gamma;
     for (int k = 0; k < 3; k++) rp.lightDisplay[k] = c->lightDisplay[k];
+    c->stageBegin(ST_RESOLVE);
     resolve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(rp, c->accVpl.p, c->accPhoton.p, c->accLight.p, n, c->resolveOut.p);
+    c->stageEnd(ST_RESOLVE);
     c->launches++;
     return cudaGetLastError();
 }

@@ -233,12 +233,15 @@ int evplp_debug_curand(evplp_handle h, uint32_t seed, uint32_t subsequence, uint
 int evplp_debug_math(evplp_handle h, int op, const float* x, const float* y, uint32_t n, float* out);
 int evplp_stats(evplp_handle h, EvplpStats* stats);
 int evplp_reset_stats(evplp_handle h);
-/* Device time (ms, CUDA events on the handle's stream) of the most recent call of each
- * stage: 0 bvh, 1 gbuffer, 2 light_trace, 3 gather, 4 splat, 5 resolve. */
+/* Device time (ms, CUDA events on the handle's stream, bracketing the stage's main kernel) of the
+ * most recent call of each stage: 0 bvh (whole build), 1 gbuffer, 2 light_trace, 3 gather, 4 splat, 5 resolve. */
 int evplp_last_stage_ms(evplp_handle h, int stage, float* ms);
 int evplp_synchronize(evplp_handle h);
 /* Number of kernel launches issued by this handle since creation (bench.py gpu_launches). */
 int evplp_launch_count(evplp_handle h, uint64_t* count);
+/* CUDA events on the handle's stream (4 slots): device-side timing of any span of calls. */
+int evplp_event_record(evplp_handle h, int slot);
+int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
 /* Tuning knobs (no reference counterpart).  "gather_chunks": number of slices the VPL list is
  * split into across thread blocks (0 = automatic; 1 = every pixel sums its VPLs in record
  * order in one thread, which makes the gather bit-identical to the scalar oracle). */
