@@ -140,6 +140,20 @@ int evplp_host_render_json(const char* jsonPath, int device) {
     )
 }
 
+// host-only taps (no device): the progressive schedule and the jitter stream of RtComPhoton
+void evplp_host_progressive_update(int32_t numIterations, float alpha, float clampingStart, uint32_t numVplLightPaths,
+                                   uint32_t numLightPaths, int32_t forceVsl, float* state /* radius, clamp, pdfMc, vslRadius, vslInvPiR2 */) {
+    RtComPhoton::ProgressiveUpdate(numIterations, alpha, clampingStart, numVplLightPaths, numLightPaths, forceVsl != 0, &state[0],
+                                   &state[1], &state[2], &state[3], &state[4]);
+}
+void evplp_host_jitter_stream(uint32_t rngOffset, uint32_t numIterations, float* out) {
+    IndependentSampler s(rngOffset);
+    for (uint32_t i = 0; i < numIterations; i++) { Vec2 v = s.nextVec2(); out[2 * i] = v.x; out[2 * i + 1] = v.y; }
+}
+int evplp_host_save_pfm(const char* path, const float* rgbTopDown, int w, int h) {
+    GUARD(FloatImage f((size_t)w, (size_t)h); memcpy(f.data(), rgbTopDown, sizeof(float) * 3 * (size_t)w * h); FloatImage::Save(f, path); return 0;)
+}
+
 float evplp_host_pfm_relmse(const char* a, const char* b) {
     try { return FloatImage::ComputeRelMse(FloatImage::LoadPFM(a), FloatImage::LoadPFM(b)); }
     catch (const std::exception& e) { g_hostErr = e.what(); return -1.f; }

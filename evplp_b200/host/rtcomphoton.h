@@ -188,6 +188,22 @@ public:
         check(evplp_set_params(mHandle, &P), "evplp_set_params");
     }
 
+    // The progressive schedule (rtcomphoton.h:1033-1063), evaluated after numIterations++.  Types as in the
+    // reference: float ratio (int + float), float sqrt, pow(int, float) in double, product rounded to float.
+    static void ProgressiveUpdate(int numIterations, float alphaProgressive, float clampingStart, uint32_t numVplLightPaths,
+                                  uint32_t numLightPaths, bool forceVsl, float* photonRadius, float* clampingValue,
+                                  float* pdfMc, float* vslRadius, float* vslInvPiRadius2) {
+        float ratio = (numIterations + alphaProgressive) / (numIterations + 1);
+        *photonRadius *= std::sqrt(ratio);
+        *clampingValue = (float)(clampingStart * std::pow((double)numIterations, (double)alphaProgressive));
+        *pdfMc = static_cast<float>(numVplLightPaths) / static_cast<float>(numLightPaths) * Math::InvPi / (*photonRadius * *photonRadius);
+        if (forceVsl) {
+            *vslRadius *= std::sqrt(ratio);
+            if (*vslRadius <= 0.008f) *vslRadius = std::max(*vslRadius, 0.008f);
+            *vslInvPiRadius2 = Math::InvPi / (*vslRadius * *vslRadius);
+        }
+    }
+
     // One pass of the loop body (rtcomphoton.h:936-1068).  Returns false when the loop must stop.
     bool iterate() {
         if (mNumIterations == mNumMaxIteration) return false;
@@ -214,16 +230,9 @@ public:
                       << " | timing: " << currentTiming - mPrevTiming << "\n";
             mPrevTiming = currentTiming;
         }
-        if (mDoProgressive) {  // :1033-1063 (types as in the reference: float ratio, double pow, float product)
-            float ratio = (mNumIterations + mAlphaProgressive) / (mNumIterations + 1);
-            mPhotonRadius *= std::sqrt(ratio);
-            mClampingValue = (float)(mClampingStart * std::pow((double)mNumIterations, (double)mAlphaProgressive));
-            mPrecomptedPdfMc = static_cast<float>(mNumVplLightPaths) / static_cast<float>(mNumLightPaths) * Math::InvPi / (mPhotonRadius * mPhotonRadius);
-            if (mForceVsl) {
-                mVslRadius *= std::sqrt(ratio);
-                if (mVslRadius <= 0.008f) mVslRadius = std::max(mVslRadius, 0.008f);
-                mVslInvPiRadius2 = Math::InvPi / (mVslRadius * mVslRadius);
-            }
+        if (mDoProgressive) {
+            ProgressiveUpdate(mNumIterations, mAlphaProgressive, mClampingStart, mNumVplLightPaths, mNumLightPaths, mForceVsl,
+                              &mPhotonRadius, &mClampingValue, &mPrecomptedPdfMc, &mVslRadius, &mVslInvPiRadius2);
         }
         if (mTimelimitMs > 0 && mMasterWatch.timeMilliSec() >= mTimelimitMs) return false;
         return true;

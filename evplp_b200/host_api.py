@@ -44,6 +44,9 @@ def load_host_library():
     lib.evplp_host_technique_final.argtypes = [_P, C.c_float, C.c_float, C.c_float, C.c_int, _P]
     lib.evplp_host_technique_destroy.argtypes = [_P]
     lib.evplp_host_render_json.argtypes = [C.c_char_p, C.c_int]
+    lib.evplp_host_progressive_update.argtypes = [C.c_int32, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, _P]
+    lib.evplp_host_jitter_stream.argtypes = [C.c_uint32, C.c_uint32, _P]
+    lib.evplp_host_save_pfm.argtypes = [C.c_char_p, _P, C.c_int, C.c_int]
     lib.evplp_host_pfm_relmse.restype = C.c_float
     lib.evplp_host_pfm_relmse.argtypes = [C.c_char_p, C.c_char_p]
     _lib = lib
