@@ -188,57 +188,85 @@ __device__ inline bool trace_any(const DevScene& sc, V3 org, V3 dir, float tmin,
 }
 
 // Any hit for a whole warp at once: the 32 rays walk the tree together with ONE shared
-// stack (in shared memory), so every node / triangle is fetched once per warp (uniform
-// address -> broadcast) and there is no divergence.  Rays of the gather are coherent
-// (neighbouring pixels, same VPL), so the union of their paths is barely larger than one
-// ray's.  `active` lanes carry a ray; returns per lane whether it is occluded.
-// Must be called by all 32 lanes.
+// stack, so every node / triangle is fetched once per warp (uniform address -> broadcast)
+// and there is no divergence.  Rays of the gather are coherent (neighbouring pixels, same
+// VPL), so the union of their paths is barely larger than one ray's.  `active` lanes carry
+// a ray; returns per lane whether it is occluded.  Must be called by all 32 lanes.
+//
+// The loop body is branch-free per lane: all four child slabs are tested with straight-line
+// code, the per-lane 4-bit result is OR-reduced over the warp with one REDUX, and every lane
+// performs the same (uniform) pushes, writing identical values to the warp's stack -- so no
+// __syncwarp is needed (a lane only ever reads back what it wrote itself).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ RaySlab make_slab_fast(V3 org, V3 dir) {
+    RaySlab s;
+    float dx = fabsf(dir.x) < 1e-30f ? copysignf(1e-30f, dir.x) : dir.x;
+    float dy = fabsf(dir.y) < 1e-30f ? copysignf(1e-30f, dir.y) : dir.y;
+    float dz = fabsf(dir.z) < 1e-30f ? copysignf(1e-30f, dir.z) : dir.z;
+    // 1-ulp reciprocal is enough: boxes are padded by ~100x the slab test's rounding error
+    s.ix = rcp_approx(dx); s.iy = rcp_approx(dy); s.iz = rcp_approx(dz);
+    s.ox = org.x * s.ix; s.oy = org.y * s.iy; s.oz = org.z * s.iz;
+    return s;
+}
+
+__device__ __forceinline__ bool slab4(const RaySlab& s, float lx, float ly, float lz, float hx, float hy, float hz,
+                                      float tmin, float tmax) {
+    const float x0 = __fmaf_rn(lx, s.ix, -s.ox), x1 = __fmaf_rn(hx, s.ix, -s.ox);
+    const float y0 = __fmaf_rn(ly, s.iy, -s.oy), y1 = __fmaf_rn(hy, s.iy, -s.oy);
+    const float z0 = __fmaf_rn(lz, s.iz, -s.oz), z1 = __fmaf_rn(hz, s.iz, -s.oz);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    return tn <= tf;
+}
+
+static_assert(BVH_WIDTH == 4, "trace_any_warp is written for 4-wide nodes");
+
 __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V3 dir, float tmin, float tmax,
                                       uint32_t* warpStack /* BVH_STACK entries in smem */, int* overflow) {
     const unsigned full = 0xffffffffu;
     bool open = active;  // still needs an answer
-    bool occluded = false;
     if (sc.numNodes == 0 || !__any_sync(full, open)) return false;
-    const RaySlab slab = make_slab(org, dir);
-    const int lane = threadIdx.x & 31;
+    const RaySlab slab = make_slab_fast(org, dir);
     int sp = 0;
     uint32_t cur = 0;
     while (true) {
         if (cur & BVH_LEAF_BIT) {
             const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
-            for (uint32_t k = 0; k < count; k++) {
-                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
+            const float4* tp = sc.triLeaf + 4 * (size_t)first;
+            bool hit = false;
+            for (uint32_t k = 0; k < count; k++, tp += 4) {
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
                 float t, be, ga;
-                if (open && tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) {
-                    occluded = true;
-                    open = false;
-                }
+                hit |= tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga);
             }
+            open = open && !hit;
             if (!__any_sync(full, open)) break;
         } else {
-            const WideNode& nd = sc.nodes[cur];
-            uint32_t push[BVH_WIDTH];
-            int np = 0;
-#pragma unroll
-            for (int c = 0; c < BVH_WIDTH; c++) {
-                float t;
-                const uint32_t cd = nd.child[c];
-                bool want = open && cd != BVH_EMPTY && slab_test(slab, nd, c, tmin, tmax, &t);
-                if (__any_sync(full, want)) push[np++] = cd;
-            }
-            if (sp + np > BVH_STACK) { *overflow = 1; np = BVH_STACK - sp; }
-            if (lane == 0) {
-                for (int j = 0; j < np; j++) warpStack[sp + j] = push[j];
-            }
-            sp += np;
-            __syncwarp();
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
+            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+            const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+            unsigned m = 0;
+            m |= (slab4(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, tmax) & (ch.x != BVH_EMPTY)) ? 1u : 0u;
+            m |= (slab4(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, tmax) & (ch.y != BVH_EMPTY)) ? 2u : 0u;
+            m |= (slab4(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, tmax) & (ch.z != BVH_EMPTY)) ? 4u : 0u;
+            m |= (slab4(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, tmax) & (ch.w != BVH_EMPTY)) ? 8u : 0u;
+            m = __reduce_or_sync(full, open ? m : 0u);  // uniform from here on
+            if (sp + 4 > BVH_STACK) { *overflow = 1; break; }
+            if (m & 1u) warpStack[sp++] = ch.x;
+            if (m & 2u) warpStack[sp++] = ch.y;
+            if (m & 4u) warpStack[sp++] = ch.z;
+            if (m & 8u) warpStack[sp++] = ch.w;
         }
         if (sp == 0) break;
         cur = warpStack[--sp];
-        __syncwarp();
     }
-    return occluded;
+    return active && !open;
 }
 
 #endif  // __CUDACC__

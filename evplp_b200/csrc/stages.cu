@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) light_trace_kernel(DevScene sc, const uin
 }
 
 // ------------------------------------------------------------------ VPL gather ----------
-constexpr int GATHER_BATCH = 128;   // VPL records staged per shared-memory batch
+constexpr int GATHER_BATCH = 32;    // VPL records staged per warp and shared-memory batch
 constexpr int GATHER_WARPS = 8;
 
 struct GatherParams {
@@ -236,9 +236,12 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32)
 gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf, const EvplpRecord* __restrict__ records,
                   const uint32_t* __restrict__ vplList, const uint32_t* __restrict__ vplCount, long long* __restrict__ acc,
                   DevStats* stats) {
-    __shared__ float4 batch[GATHER_BATCH * 6];
+    // Every warp stages its own VPL batches (no block-wide barrier: warps whose pixels are
+    // culled by the cosine test run ahead instead of waiting for the slowest warp of the block).
+    __shared__ float4 batchAll[GATHER_WARPS][GATHER_BATCH * 6];
     __shared__ uint32_t stacks[GATHER_WARPS][BVH_STACK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* batch = batchAll[warp];
     const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = gp.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = x < gp.x1 && y < gp.y1;
@@ -251,19 +254,20 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
 
     const uint32_t total = *vplCount;
     const uint32_t per = (total + gp.numChunks - 1) / gp.numChunks;
-    const uint32_t begin = min(total, blockIdx.z * per), end = min(total, begin + per);
+    const uint32_t begin = min(total, blockIdx.z * per);
+    const uint32_t end = __any_sync(0xffffffffu, valid) ? min(total, begin + per) : begin;
 
     V3 result = v3s(0.0f);
     unsigned rays = 0;
     int ovf = 0;
     for (uint32_t base = begin; base < end; base += GATHER_BATCH) {
         const uint32_t nb = min((uint32_t)GATHER_BATCH, end - base);
-        __syncthreads();
-        for (uint32_t k = threadIdx.x; k < nb * 6; k += blockDim.x) {
+        __syncwarp();
+        for (uint32_t k = lane; k < nb * 6; k += 32) {
             const uint32_t r = vplList[base + k / 6];
-            batch[k] = reinterpret_cast<const float4*>(records + r)[k % 6];
+            batch[k] = __ldg(reinterpret_cast<const float4*>(records + r) + k % 6);
         }
-        __syncthreads();
+        __syncwarp();
         for (uint32_t j = 0; j < nb; j++) {
             const float4 a = batch[j * 6], b = batch[j * 6 + 1];
             const V3 vpos = v3(a.x, a.y, a.z), vn = v3(b.x, b.y, b.z);
