@@ -196,6 +196,10 @@ def run_gpu(args):
     def ck(rc, what):
         capi.check(lib, rc, what)
 
+    for kv in args.opt:
+        name, value = kv.split("=")
+        ck(lib.evplp_set_option(h, name.encode(), int(value)), "set_option")
+
     def barrier():
         ck(lib.evplp_synchronize(h), "sync")
         torch.cuda.synchronize()
@@ -345,6 +349,7 @@ def main():
     ap.add_argument("--vpl-paths", type=int, default=None, help="override numVplLightPaths (profiling only)")
     ap.add_argument("--light-paths", type=int, default=None, help="override numLightPaths (profiling only)")
     ap.add_argument("--res", default=None, help="override WxH (profiling only)")
+    ap.add_argument("--opt", action="append", default=[], help="evplp_set_option name=value (tuning experiments)")
     args = ap.parse_args()
     global RES_X, RES_Y, WORKLOAD
     if args.vpl_paths is not None:

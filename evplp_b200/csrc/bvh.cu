@@ -226,8 +226,9 @@ __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint
     WideNode nd;
     for (int k = 0; k < BVH_WIDTH; k++) {
         if (k >= nc) {
-            nd.lox[k] = nd.loy[k] = nd.loz[k] = INFINITY;
-            nd.hix[k] = nd.hiy[k] = nd.hiz[k] = -INFINITY;
+            // empty slot: a huge FINITE box (no inf * 0 = NaN in the sign-masked slab test) that no ray ever enters
+            nd.lox[k] = nd.loy[k] = nd.loz[k] = BVH_EMPTY_COORD;
+            nd.hix[k] = nd.hiy[k] = nd.hiz[k] = BVH_EMPTY_COORD;
             nd.child[k] = BVH_EMPTY;
             continue;
         }
@@ -262,8 +263,8 @@ __global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const 
     for (int i = 0; i < n; i++)
         for (int k = 0; k < 3; k++) { b[k] = fminf(b[k], primLo[3 * i + k]); b[3 + k] = fmaxf(b[3 + k], primHi[3 * i + k]); }
     for (int k = 0; k < BVH_WIDTH; k++) {
-        nd.lox[k] = nd.loy[k] = nd.loz[k] = INFINITY;
-        nd.hix[k] = nd.hiy[k] = nd.hiz[k] = -INFINITY;
+        nd.lox[k] = nd.loy[k] = nd.loz[k] = BVH_EMPTY_COORD;
+        nd.hix[k] = nd.hiy[k] = nd.hiz[k] = BVH_EMPTY_COORD;
         nd.child[k] = BVH_EMPTY;
     }
     nd.lox[0] = b[0] - pad; nd.loy[0] = b[1] - pad; nd.loz[0] = b[2] - pad;

@@ -11,6 +11,7 @@ using namespace evplp;
 
 namespace evplp {
 int g_gatherChunks = 0;
+int g_gatherMinBlocks = 3;
 }
 
 static thread_local std::string g_err;
@@ -590,6 +591,7 @@ int evplp_event_elapsed_ms(evplp_handle c, int slotA, int slotB, float* ms) {
 int evplp_set_option(evplp_handle c, const char* name, int value) {
     NEED(c != nullptr && name != nullptr, "evplp_set_option: NULL argument");
     if (strcmp(name, "gather_chunks") == 0) { evplp::g_gatherChunks = value; return EVPLP_OK; }
+    if (strcmp(name, "gather_min_blocks") == 0) { evplp::g_gatherMinBlocks = value; return EVPLP_OK; }
     return fail(EVPLP_ERR_INVALID, std::string("evplp_set_option: unknown option ") + name);
 }
 

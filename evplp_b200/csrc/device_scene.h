@@ -26,6 +26,7 @@ constexpr int BVH_LEAF_MAX = 4;             // triangles per leaf child
 constexpr uint32_t BVH_EMPTY = 0x7fffffffu;
 constexpr uint32_t BVH_LEAF_BIT = 0x80000000u;
 constexpr int BVH_STACK = 96;
+constexpr float BVH_EMPTY_COORD = 3.0e38f;   // box of an empty child slot (finite, beyond any scene)
 
 struct alignas(128) WideNode {
     float lox[BVH_WIDTH], loy[BVH_WIDTH], loz[BVH_WIDTH];
@@ -226,13 +227,65 @@ __device__ __forceinline__ bool slab4(const RaySlab& s, float lx, float ly, floa
 
 static_assert(BVH_WIDTH == 4, "trace_any_warp is written for 4-wide nodes");
 
+// ---- warp-cooperative any-hit traversal -------------------------------------------------------
+// Shared-memory stack addressed by a 32-bit shared-window byte address kept in a register.
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Per-ray constants of the sign-masked slab test.  For each axis (a, b) = (inv, 0) when the
+// direction component is >= 0 and (0, inv) otherwise, so that
+//     t_entry = lo * a + hi * b - org * inv        t_exit = lo * b + hi * a - org * inv
+// select the entry / exit plane with FMAs only (the FMA pipe is idle next to the ALU pipe that
+// executes min/max), per lane, with no sortedness requirement and no address arithmetic.
+struct RaySlabM {
+    float ax, ay, az, bx, by, bz, ox, oy, oz;
+};
+__device__ __forceinline__ RaySlabM make_slab_masked(V3 org, V3 dir) {
+    const RaySlab s = make_slab_fast(org, dir);
+    RaySlabM m;
+    m.ax = s.ix >= 0.f ? s.ix : 0.f; m.bx = s.ix >= 0.f ? 0.f : s.ix;
+    m.ay = s.iy >= 0.f ? s.iy : 0.f; m.by = s.iy >= 0.f ? 0.f : s.iy;
+    m.az = s.iz >= 0.f ? s.iz : 0.f; m.bz = s.iz >= 0.f ? 0.f : s.iz;
+    m.ox = -s.ox; m.oy = -s.oy; m.oz = -s.oz;
+    return m;
+}
+__device__ __forceinline__ bool slab_masked(const RaySlabM& s, float lx, float ly, float lz, float hx, float hy, float hz,
+                                            float tmin, float tmax) {
+    const float nx = __fmaf_rn(lx, s.ax, __fmaf_rn(hx, s.bx, s.ox)), fx = __fmaf_rn(lx, s.bx, __fmaf_rn(hx, s.ax, s.ox));
+    const float ny = __fmaf_rn(ly, s.ay, __fmaf_rn(hy, s.by, s.oy)), fy = __fmaf_rn(ly, s.by, __fmaf_rn(hy, s.ay, s.oy));
+    const float nz = __fmaf_rn(lz, s.az, __fmaf_rn(hz, s.bz, s.oz)), fz = __fmaf_rn(lz, s.bz, __fmaf_rn(hz, s.az, s.oz));
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float tf = fminf(fminf(fx, fy), fminf(fz, tmax));
+    return tn <= tf;
+}
+
+static_assert(BVH_WIDTH == 4, "the warp traversal is written for 4-wide nodes");
+
+// Any hit for a whole warp at once: the 32 rays walk the tree together with ONE shared
+// stack, so every node / triangle is fetched once per warp (uniform address -> broadcast)
+// and there is no divergence.  Rays of the gather are coherent (neighbouring pixels, same
+// VPL), so the union of their paths is barely larger than one ray's.  `active` lanes carry
+// a ray; returns per lane whether it is occluded.  Must be called by all 32 lanes.
+//
+// The loop body is branch-free per lane; the four per-child results are OR-reduced with votes
+// and every lane performs the same (uniform) pushes, writing identical values to the warp's
+// stack -- so no __syncwarp is needed (a lane only reads back slots it wrote itself; the votes
+// keep the lanes within one iteration of each other).  Empty child slots hold huge finite
+// boxes that are never entered, so the child words need no test.
 __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V3 dir, float tmin, float tmax,
                                       uint32_t* warpStack /* BVH_STACK entries in smem */, int* overflow) {
     const unsigned full = 0xffffffffu;
     bool open = active;  // still needs an answer
-    if (sc.numNodes == 0 || !__any_sync(full, open)) return false;
-    const RaySlab slab = make_slab_fast(org, dir);
-    int sp = 0;
+    if (sc.numNodes == 0 || !__any_sync(full, active)) return false;
+    const RaySlabM slab = make_slab_masked(org, dir);
+    const uint32_t stackBase = (uint32_t)__cvta_generic_to_shared(warpStack);
+    uint32_t sp = stackBase;
     uint32_t cur = 0;
     while (true) {
         if (cur & BVH_LEAF_BIT) {
@@ -251,20 +304,22 @@ __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V
             const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
             const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
             const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
-            unsigned m = 0;
-            m |= (slab4(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, tmax) & (ch.x != BVH_EMPTY)) ? 1u : 0u;
-            m |= (slab4(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, tmax) & (ch.y != BVH_EMPTY)) ? 2u : 0u;
-            m |= (slab4(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, tmax) & (ch.z != BVH_EMPTY)) ? 4u : 0u;
-            m |= (slab4(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, tmax) & (ch.w != BVH_EMPTY)) ? 8u : 0u;
-            m = __reduce_or_sync(full, open ? m : 0u);  // uniform from here on
-            if (sp + 4 > BVH_STACK) { *overflow = 1; break; }
-            if (m & 1u) warpStack[sp++] = ch.x;
-            if (m & 2u) warpStack[sp++] = ch.y;
-            if (m & 4u) warpStack[sp++] = ch.z;
-            if (m & 8u) warpStack[sp++] = ch.w;
+            const bool h0 = slab_masked(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, tmax);
+            const bool h1 = slab_masked(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, tmax);
+            const bool h2 = slab_masked(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, tmax);
+            const bool h3 = slab_masked(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, tmax);
+            // warp-uniform from here on: every lane performs the same pushes (identical values)
+            const bool p0 = __any_sync(full, h0 & open), p1 = __any_sync(full, h1 & open);
+            const bool p2 = __any_sync(full, h2 & open), p3 = __any_sync(full, h3 & open);
+            if (sp + 16u > stackBase + 4u * BVH_STACK) { *overflow = 1; break; }
+            if (p0) { st_shared_u32(sp, ch.x); sp += 4u; }
+            if (p1) { st_shared_u32(sp, ch.y); sp += 4u; }
+            if (p2) { st_shared_u32(sp, ch.z); sp += 4u; }
+            if (p3) { st_shared_u32(sp, ch.w); sp += 4u; }
         }
-        if (sp == 0) break;
-        cur = warpStack[--sp];
+        if (sp == stackBase) break;
+        sp -= 4u;
+        cur = ld_shared_u32(sp);
     }
     return active && !open;
 }

@@ -232,7 +232,8 @@ struct GatherParams {
     unsigned numLightPaths, numVplLightPaths, B1;
 };
 
-__global__ void __launch_bounds__(GATHER_WARPS * 32)
+template <int MINB>
+__global__ void __launch_bounds__(GATHER_WARPS * 32, MINB)
 gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf, const EvplpRecord* __restrict__ records,
                   const uint32_t* __restrict__ vplList, const uint32_t* __restrict__ vplCount, long long* __restrict__ acc,
                   DevStats* stats) {
@@ -708,7 +709,8 @@ static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
     return g;
 }
 
-extern int g_gatherChunks;  // capi.cu (0 = automatic)
+extern int g_gatherChunks;     // capi.cu (0 = automatic)
+extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
 
 cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     const EvplpParams& P = c->params;
@@ -763,8 +765,11 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         c->launches++;
     }
     c->stageBegin(ST_GATHER);
-    gather_vpl_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount,
-                                                                  c->accVpl.p, c->devStats.p);
+    switch (g_gatherMinBlocks) {
+        case 2: gather_vpl_kernel<2><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+        case 4: gather_vpl_kernel<4><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+        default: gather_vpl_kernel<3><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+    }
     c->stageEnd(ST_GATHER);
     c->launches++;
     return cudaGetLastError();
