@@ -12,6 +12,9 @@ using namespace evplp;
 namespace evplp {
 int g_gatherChunks = 0;
 int g_gatherMinBlocks = 3;
+int g_splatGroup = 0;
+int g_splatMode = 0;
+int g_splatMaxEntries = 256 * 1024 * 1024;
 }
 
 static thread_local std::string g_err;
@@ -110,7 +113,7 @@ int evplp_destroy(evplp_handle c) {
     c->leafParent.release(); c->rangeFirst.release(); c->rangeLast.release(); c->nodeBounds.release();
     c->refitFlags.release(); c->nodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
     c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->records.release();
-    c->vplList.release(); c->photonList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
+    c->vplList.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
     c->accPhoton.release(); c->accLight.release(); c->resolveOut.release(); c->devStats.release();
     if (c->resolvePinned) cudaFreeHost(c->resolvePinned);
     for (int s = 0; s < ST_COUNT; s++) { cudaEventDestroy(c->stageA[s]); cudaEventDestroy(c->stageB[s]); }
@@ -592,6 +595,9 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
     NEED(c != nullptr && name != nullptr, "evplp_set_option: NULL argument");
     if (strcmp(name, "gather_chunks") == 0) { evplp::g_gatherChunks = value; return EVPLP_OK; }
     if (strcmp(name, "gather_min_blocks") == 0) { evplp::g_gatherMinBlocks = value; return EVPLP_OK; }
+    if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }
+    if (strcmp(name, "splat_mode") == 0) { evplp::g_splatMode = value; return EVPLP_OK; }
+    if (strcmp(name, "splat_max_entries") == 0) { evplp::g_splatMaxEntries = value; return EVPLP_OK; }
     return fail(EVPLP_ERR_INVALID, std::string("evplp_set_option: unknown option ") + name);
 }
 

@@ -86,6 +86,8 @@ struct EvplpContext {
     uint32_t recordsFirstPath = 0;
     evplp::DevBuf<uint32_t> vplList;              // indices of usable VPL records (gather prefix)
     evplp::DevBuf<uint32_t> photonList;           // indices of usable photon records
+    evplp::DevBuf<float4> splatPrep;              // per-photon constants of the fragment shader (5 float4 each)
+    evplp::DevBuf<uint32_t> tileCount, tileOffset, tileCursor, tileList;  // photon bins of the tiled splat
 
     evplp::DevBuf<float4> gbuf;                   // 4 planes of W*H
     evplp::DevBuf<int32_t> gprim;

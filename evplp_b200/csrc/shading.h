@@ -231,50 +231,72 @@ struct SplatUniforms {
     unsigned numLightPaths;
 };
 
-// Fragment shader body (photonsplatinstanced.frag:146-240) for photon `ph` with predecessor
-// `prev` on surface texel `sf`.  The radius test is done by the caller.  Returns false when
-// the fragment is discarded.
-EVPLP_HD bool splat_fragment(const SplatUniforms& U, const Surface& sf, const Vertex& ph, const Vertex& prev, V3* color) {
+// The fragment shader (photonsplatinstanced.frag:146-240) split into its per-photon part
+// (everything that does not depend on the shaded texel) and its per-fragment part, with the
+// arithmetic of each expression unchanged.
+struct SplatPhoton {
+    V3 pos, w12, flux;   // photon position, direction to its predecessor, flux
+    float weight;        // modes 1-3: MIS weight h(mixPdfA, pdfMc)
+    float dist2;         // |p_{k-1} - p_k|^2 (modes 4, 5)
+    V3 prevN;            // predecessor normal (modes 4, 5)
+    V3 brdf2;            // BRDF at the predecessor (mode 5)
+    int live;            // mixPdfW > 0
+};
+
+EVPLP_HD SplatPhoton splat_prepare(const SplatUniforms& U, const Vertex& ph, const Vertex& prev) {
+    SplatPhoton sp;
+    sp.pos = ph.pos; sp.flux = ph.flux;
     V3 v12 = prev.pos - ph.pos;
     V3 w12 = normalize(v12);
-    V3 w10 = normalize(U.cameraPosition - sf.pos);
-    V3 brdf1 = glsl_lambert_eval(w10, w12, sf.normal, sf.kd) + glsl_phong_eval(w10, w12, sf.normal, sf.ks, sf.exponent);
-
+    sp.w12 = w12;
     float mixPdfW = glsl_lambert_pdf_w(prev.normal, -w12) * prev.pSel;
     mixPdfW += glsl_phong_pdf_w(prev.normal, -w12, prev.fluxDir, prev.ks, prev.exponent) * (1.0f - prev.pSel);
+    sp.live = (mixPdfW > 0.0f) ? 1 : 0;
+    sp.weight = 1.0f; sp.dist2 = dot(v12, v12); sp.prevN = prev.normal; sp.brdf2 = v3s(0.0f);
+    if (U.misMode >= 1 && U.misMode <= 3) {
+        float mixPdfA = det_div(mixPdfW * det_max(dot(ph.normal, w12), 0.0f), dot(v12, v12));
+        sp.weight = U.misMode == 1 ? balance_heuristic(mixPdfA, U.pdfMc)
+                  : U.misMode == 2 ? max_heuristic(mixPdfA, U.pdfMc) : power_heuristic2(mixPdfA, U.pdfMc);
+    } else if (U.misMode == 5) {
+        sp.brdf2 = glsl_lambert_eval(-w12, prev.fluxDir, prev.normal, prev.kd) +
+                   glsl_phong_eval(-w12, prev.fluxDir, prev.normal, prev.ks, prev.exponent);
+    }
+    return sp;
+}
 
-    const float invR2 = det_div(1.0f, U.radius * U.radius);      // rtcomphoton.h:819
-    const float invN = det_div(1.0f, (float)U.numLightPaths);    // rtcomphoton.h:820
-
-    if (!(mixPdfW > 0.0f)) {
+// w10 = normalize(cameraPosition - sf.pos); invR2 = 1 / r^2 (rtcomphoton.h:819); invN = 1 / numLightPaths (:820).
+// The radius test is done by the caller.  Returns false when the fragment is discarded.
+EVPLP_HD bool splat_shade(const SplatUniforms& U, float invR2, float invN, const Surface& sf, V3 w10, const SplatPhoton& sp, V3* color) {
+    V3 brdf1 = glsl_lambert_eval(w10, sp.w12, sf.normal, sf.kd) + glsl_phong_eval(w10, sp.w12, sf.normal, sf.ks, sf.exponent);
+    if (!sp.live) {
         *color = v3s(0.0f);
         return true;
     }
     if (U.misMode == 0) {
-        *color = brdf1 * (kInvPi * invR2) * ph.flux * invN;
+        *color = brdf1 * (kInvPi * invR2) * sp.flux * invN;
     } else if (U.misMode <= 3) {
-        float mixPdfA = det_div(mixPdfW * det_max(dot(ph.normal, w12), 0.0f), dot(v12, v12));
-        float weight = U.misMode == 1 ? balance_heuristic(mixPdfA, U.pdfMc)
-                     : U.misMode == 2 ? max_heuristic(mixPdfA, U.pdfMc) : power_heuristic2(mixPdfA, U.pdfMc);
-        *color = brdf1 * (kInvPi * invR2) * ph.flux * invN * weight;
+        *color = brdf1 * (kInvPi * invR2) * sp.flux * invN * sp.weight;
     } else {
-        float distance2 = dot(v12, v12);
-        float cosCos = det_max(dot(sf.normal, w12), 0.0f) * det_max(-dot(prev.normal, w12), 0.0f);
+        float cosCos = det_max(dot(sf.normal, sp.w12), 0.0f) * det_max(-dot(sp.prevN, sp.w12), 0.0f);
         if (cosCos <= 0.0f) return false;
-        float geometryTerm = det_div(cosCos, distance2);
+        float geometryTerm = det_div(cosCos, sp.dist2);
         if (U.misMode == 4) {
-            *color = brdf1 * (kInvPi * invR2) * ph.flux * invN *
-                     det_max(geometryTerm - U.clampingValue, 0.0f) / geometryTerm;
+            *color = brdf1 * (kInvPi * invR2) * sp.flux * invN * det_max(geometryTerm - U.clampingValue, 0.0f) / geometryTerm;
         } else {
-            V3 brdf2 = glsl_lambert_eval(-w12, prev.fluxDir, prev.normal, prev.kd) +
-                       glsl_phong_eval(-w12, prev.fluxDir, prev.normal, prev.ks, prev.exponent);
-            V3 num = vmax((brdf1 * brdf2 * geometryTerm) - v3s(U.clampingValue), v3s(0.0f));
-            V3 den = geometryTerm * brdf2;
-            V3 pre = (kInvPi * invR2) * ph.flux * invN;
+            V3 num = vmax((brdf1 * sp.brdf2 * geometryTerm) - v3s(U.clampingValue), v3s(0.0f));
+            V3 den = geometryTerm * sp.brdf2;
+            V3 pre = (kInvPi * invR2) * sp.flux * invN;
             *color = v3(det_div(pre.x * num.x, den.x), det_div(pre.y * num.y, den.y), det_div(pre.z * num.z, den.z));
         }
     }
     return true;
+}
+
+EVPLP_HD bool splat_fragment(const SplatUniforms& U, const Surface& sf, const Vertex& ph, const Vertex& prev, V3* color) {
+    const SplatPhoton sp = splat_prepare(U, ph, prev);
+    const float invR2 = det_div(1.0f, U.radius * U.radius);
+    const float invN = det_div(1.0f, (float)U.numLightPaths);
+    return splat_shade(U, invR2, invN, sf, normalize(U.cameraPosition - sf.pos), sp, color);
 }
 
 // Q31.32 fixed point of the accumulation layers; non-finite / huge values are dropped.

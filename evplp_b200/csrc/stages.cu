@@ -10,6 +10,7 @@
 //   resolve_kernel       replaces runFinalProgram + final.frag                     (rtcomphoton.h:756-787)
 //
 // Compiled with -fmad=false: all shading arithmetic rounds exactly as written (shading.h).
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <curand_kernel.h>
@@ -570,8 +571,12 @@ __device__ __forceinline__ void splat_rect(const SplatParams& sp, V3 p, int* rx0
     }
 }
 
-// One warp per usable photon; lanes sweep the photon's screen rectangle and scatter-add
-// Q31.32 fixed-point contributions (order-independent => deterministic).
+// A group of G lanes (G = 1, 8 or 32) per usable photon: the group sweeps the photon's conservative
+// screen rectangle, tests |p - pos(x)|^2 <= r^2 per texel and scatter-adds Q31.32 fixed-point
+// contributions (order-independent => deterministic).  G is picked per launch from the expected
+// footprint: tiny footprints (a few pixels) waste 31 of 32 lanes with a warp per photon, large
+// ones (hundreds of pixels) want the whole warp.
+template <int G>
 __global__ void __launch_bounds__(256) splat_kernel(SplatParams sp, const float4* __restrict__ gbuf,
                                                     const int32_t* __restrict__ gprim,
                                                     const EvplpRecord* __restrict__ records,
@@ -579,30 +584,38 @@ __global__ void __launch_bounds__(256) splat_kernel(SplatParams sp, const float4
                                                     const uint32_t* __restrict__ photonCount, long long* __restrict__ acc,
                                                     DevStats* stats) {
     const int lane = threadIdx.x & 31;
-    const uint32_t warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    const int sub = lane % G;
+    const uint32_t groupId = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint32_t numGroups = (gridDim.x * blockDim.x) / G;
     const uint32_t total = *photonCount;
     const size_t n = (size_t)sp.W * sp.H;
     const float r2 = sp.U.radius * sp.U.radius;
     unsigned frags = 0;
-    for (uint32_t w = warpId; w < total; w += numWarps) {
+    for (uint32_t w = groupId; w < total; w += numGroups) {
         const uint32_t k = photonList[w];
         const float4* r = reinterpret_cast<const float4*>(records + k);
-        const Vertex ph = load_vertex(r);
+        const float4 r0 = __ldg(r);
+        const V3 ppos = v3(r0.x, r0.y, r0.z);
         int rx0, ry0, rx1, ry1;
-        splat_rect(sp, ph.pos, &rx0, &ry0, &rx1, &ry1);
+        splat_rect(sp, ppos, &rx0, &ry0, &rx1, &ry1);
         rx0 = max(rx0, sp.x0); ry0 = max(ry0, sp.y0); rx1 = min(rx1, sp.x1); ry1 = min(ry1, sp.y1);
         const int rw = rx1 - rx0, rh = ry1 - ry0;
         if (rw <= 0 || rh <= 0) continue;
-        const Vertex prev = load_vertex(r - 6);  // record k-1: same path (a photon is never a path's first record)
         const int area = rw * rh;
-        for (int t = lane; t < area; t += 32) {
-            const int px = rx0 + t % rw, py = ry0 + t / rw;
-            const size_t i = (size_t)py * sp.W + px;
-            if (gprim[i] < 0) continue;
-            const float4 gp0 = gbuf[i];
-            const V3 d = ph.pos - v3(gp0.x, gp0.y, gp0.z);
+        bool loaded = false;
+        Vertex ph, prev;
+        for (int t = sub; t < area; t += G) {
+            const int py = t / rw, px = t - py * rw;
+            const size_t i = (size_t)(ry0 + py) * sp.W + (rx0 + px);
+            const float4 gp0 = __ldg(gbuf + i);
+            const V3 d = ppos - v3(gp0.x, gp0.y, gp0.z);
             if (dot(d, d) > r2) continue;
+            if (__ldg(gprim + i) < 0) continue;  // background texel (position 0): no surface
+            if (!loaded) {
+                ph = load_vertex(r);
+                prev = load_vertex(r - 6);  // record k-1: same path (a photon is never a path's first record)
+                loaded = true;
+            }
             float gw;
             const Surface sf = load_surface(gbuf, n, i, &gw);
             V3 color;
@@ -616,6 +629,132 @@ __global__ void __launch_bounds__(256) splat_kernel(SplatParams sp, const float4
     }
     for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
     if (lane == 0 && frags) atomicAdd(&stats->splatFragments, (unsigned long long)frags);
+}
+
+// ---- tiled photon splat ------------------------------------------------------------------------
+// Photons are binned to 16x16-pixel screen tiles; one block per (tile, photon chunk) keeps its 256
+// G-buffer texels in registers, streams the tile's photons through shared memory, tests
+// |p - pos(x)|^2 <= r^2 per (texel, photon), shades the hits and accumulates Q31.32 in registers:
+// ONE accumulator update per pixel per launch, no per-fragment atomics, G-buffer read once.
+// The per-photon half of the fragment shader (splat_prepare) runs once per photon in the binning pass.
+constexpr int SPLAT_TILE = 16;
+constexpr int SPLAT_BATCH = 64;      // photons staged per shared-memory batch
+constexpr int SPLAT_CHUNK = 2048;    // photons of one tile handled by one block
+constexpr int SPLAT_PREP_F4 = 5;     // float4s per prepared photon
+
+struct TileGrid {
+    int tx0, ty0, nx, ny;            // first tile (in tile units) and tile counts covering the launch rectangle
+};
+
+__device__ __forceinline__ void photon_tile_range(const SplatParams& sp, const TileGrid& tg, V3 pos, int* a0, int* b0, int* a1, int* b1) {
+    int rx0, ry0, rx1, ry1;
+    splat_rect(sp, pos, &rx0, &ry0, &rx1, &ry1);
+    rx0 = max(rx0, sp.x0); ry0 = max(ry0, sp.y0); rx1 = min(rx1, sp.x1); ry1 = min(ry1, sp.y1);
+    if (rx1 <= rx0 || ry1 <= ry0) { *a0 = *b0 = 0; *a1 = *b1 = -1; return; }
+    *a0 = rx0 / SPLAT_TILE - tg.tx0; *a1 = (rx1 - 1) / SPLAT_TILE - tg.tx0;
+    *b0 = ry0 / SPLAT_TILE - tg.ty0; *b1 = (ry1 - 1) / SPLAT_TILE - tg.ty0;
+}
+
+__global__ void splat_prepare_kernel(SplatParams sp, TileGrid tg, const EvplpRecord* __restrict__ records,
+                                     const uint32_t* __restrict__ photonList, const uint32_t* __restrict__ photonCount,
+                                     float4* __restrict__ prep, uint32_t* __restrict__ tileCount) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= *photonCount) return;
+    const float4* r = reinterpret_cast<const float4*>(records + photonList[w]);
+    const Vertex ph = load_vertex(r), prev = load_vertex(r - 6);  // record k-1: same path
+    const SplatPhoton q = splat_prepare(sp.U, ph, prev);
+    float4* o = prep + (size_t)w * SPLAT_PREP_F4;
+    o[0] = make_float4(q.pos.x, q.pos.y, q.pos.z, __int_as_float(q.live));
+    o[1] = make_float4(q.w12.x, q.w12.y, q.w12.z, q.weight);
+    o[2] = make_float4(q.flux.x, q.flux.y, q.flux.z, q.dist2);
+    o[3] = make_float4(q.prevN.x, q.prevN.y, q.prevN.z, 0.f);
+    o[4] = make_float4(q.brdf2.x, q.brdf2.y, q.brdf2.z, 0.f);
+    int a0, b0, a1, b1;
+    photon_tile_range(sp, tg, q.pos, &a0, &b0, &a1, &b1);
+    for (int b = b0; b <= b1; b++)
+        for (int a = a0; a <= a1; a++) atomicAdd(&tileCount[b * tg.nx + a], 1u);
+}
+
+__global__ void splat_fill_kernel(SplatParams sp, TileGrid tg, const float4* __restrict__ prep, const uint32_t* __restrict__ photonCount,
+                                  const uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor,
+                                  uint32_t* __restrict__ tileList) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= *photonCount) return;
+    const float4 p0 = prep[(size_t)w * SPLAT_PREP_F4];
+    int a0, b0, a1, b1;
+    photon_tile_range(sp, tg, v3(p0.x, p0.y, p0.z), &a0, &b0, &a1, &b1);
+    for (int b = b0; b <= b1; b++)
+        for (int a = a0; a <= a1; a++) {
+            const int t = b * tg.nx + a;
+            tileList[tileOffset[t] + atomicAdd(&tileCursor[t], 1u)] = w;
+        }
+}
+
+__global__ void __launch_bounds__(256) splat_tile_kernel(SplatParams sp, TileGrid tg, const float4* __restrict__ gbuf,
+                                                         const int32_t* __restrict__ gprim, const float4* __restrict__ prep,
+                                                         const uint32_t* __restrict__ tileOffset, const uint32_t* __restrict__ tileList,
+                                                         long long* __restrict__ acc, int useAtomics, DevStats* stats) {
+    __shared__ float4 batch[SPLAT_BATCH * SPLAT_PREP_F4];
+    const int tile = blockIdx.y * tg.nx + blockIdx.x;
+    const uint32_t first = tileOffset[tile], count = tileOffset[tile + 1] - first;
+    const uint32_t begin = blockIdx.z * SPLAT_CHUNK;
+    if (begin >= count) return;
+    const uint32_t end = min(count, begin + SPLAT_CHUNK);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = (tg.tx0 + blockIdx.x) * SPLAT_TILE + (warp & 1) * 8 + (lane & 7);
+    const int y = (tg.ty0 + blockIdx.y) * SPLAT_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = x >= sp.x0 && x < sp.x1 && y >= sp.y0 && y < sp.y1;
+    const size_t n = (size_t)sp.W * sp.H;
+    const size_t i = inside ? (size_t)y * sp.W + x : 0;
+    float gw;
+    const Surface sf = load_surface(gbuf, n, i, &gw);
+    const bool valid = inside && gprim[i] >= 0;
+    const V3 w10 = normalize(sp.U.cameraPosition - sf.pos);
+    const float r2 = sp.U.radius * sp.U.radius;
+    const float invR2 = det_div(1.0f, sp.U.radius * sp.U.radius);
+    const float invN = det_div(1.0f, (float)sp.U.numLightPaths);
+    long long a0 = 0, a1 = 0, a2 = 0;
+    unsigned frags = 0;
+    for (uint32_t base = begin; base < end; base += SPLAT_BATCH) {
+        const uint32_t nb = min((uint32_t)SPLAT_BATCH, end - base);
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < nb * SPLAT_PREP_F4; k += blockDim.x)
+            batch[k] = __ldg(prep + (size_t)tileList[first + base + k / SPLAT_PREP_F4] * SPLAT_PREP_F4 + k % SPLAT_PREP_F4);
+        __syncthreads();
+        for (uint32_t j = 0; j < nb; j++) {
+            const float4 p0 = batch[j * SPLAT_PREP_F4];
+            const V3 d = v3(p0.x, p0.y, p0.z) - sf.pos;
+            if (!valid || dot(d, d) > r2) continue;
+            const float4 p1 = batch[j * SPLAT_PREP_F4 + 1], p2 = batch[j * SPLAT_PREP_F4 + 2], p3 = batch[j * SPLAT_PREP_F4 + 3],
+                         p4 = batch[j * SPLAT_PREP_F4 + 4];
+            SplatPhoton q;
+            q.pos = v3(p0.x, p0.y, p0.z); q.live = __float_as_int(p0.w);
+            q.w12 = v3(p1.x, p1.y, p1.z); q.weight = p1.w;
+            q.flux = v3(p2.x, p2.y, p2.z); q.dist2 = p2.w;
+            q.prevN = v3(p3.x, p3.y, p3.z); q.brdf2 = v3(p4.x, p4.y, p4.z);
+            V3 color;
+            if (!splat_shade(sp.U, invR2, invN, sf, w10, q, &color)) continue;
+            frags++;
+            a0 += to_fixed(color.x); a1 += to_fixed(color.y); a2 += to_fixed(color.z);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) frags += __shfl_xor_sync(0xffffffffu, frags, o);
+    if (lane == 0 && frags) atomicAdd(&stats->splatFragments, (unsigned long long)frags);
+    if (!valid) return;
+    if (useAtomics) {
+        if (a0) atomicAdd(reinterpret_cast<unsigned long long*>(acc + i * 3), (unsigned long long)a0);
+        if (a1) atomicAdd(reinterpret_cast<unsigned long long*>(acc + i * 3 + 1), (unsigned long long)a1);
+        if (a2) atomicAdd(reinterpret_cast<unsigned long long*>(acc + i * 3 + 2), (unsigned long long)a2);
+    } else {
+        acc[i * 3] += a0; acc[i * 3 + 1] += a1; acc[i * 3 + 2] += a2;
+    }
+}
+
+__global__ void tile_summary_kernel(const uint32_t* __restrict__ tileCount, int numTiles, uint32_t* __restrict__ out /* [0] max */) {
+    uint32_t m = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < numTiles; t += gridDim.x * blockDim.x) m = max(m, tileCount[t]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 // ------------------------------------------------------------------ light / resolve -----
@@ -710,6 +849,9 @@ static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
 }
 
 extern int g_gatherChunks;     // capi.cu (0 = automatic)
+extern int g_splatGroup;       // capi.cu: lanes per photon in the scatter splat (0 = 32; 1 / 8 / 32)
+extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatter splat
+extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
 extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
 
 cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
@@ -795,13 +937,55 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
     sp.camFwd = v3p(P.camForward); sp.camRight = v3p(P.camRight); sp.camUp = v3p(P.camUp);
     sp.tanX = P.tanHalfFovX; sp.tanY = P.tanHalfFovY; sp.jx = P.jitter[0]; sp.jy = P.jitter[1]; sp.nearD = P.nearDist;
     sp.x0 = t.x0; sp.y0 = t.y0; sp.x1 = t.x1; sp.y1 = t.y1; sp.W = c->W; sp.H = c->H;
-    const uint32_t warpsWanted = count;
-    uint32_t blocks = (warpsWanted + 7) / 8;
-    const uint32_t maxBlocks = 148u * 8u * 4u;
+    if (g_splatMode != 1) {
+        // ---- tiled path: bin -> scan -> fill -> per-tile accumulation
+        TileGrid tg;
+        tg.tx0 = t.x0 / SPLAT_TILE; tg.ty0 = t.y0 / SPLAT_TILE;
+        tg.nx = (t.x1 - 1) / SPLAT_TILE - tg.tx0 + 1; tg.ny = (t.y1 - 1) / SPLAT_TILE - tg.ty0 + 1;
+        const int numTiles = tg.nx * tg.ny;
+        e = c->splatPrep.reserve((size_t)count * SPLAT_PREP_F4); if (e != cudaSuccess) return e;
+        e = c->tileCount.reserve((size_t)numTiles + 1); if (e != cudaSuccess) return e;
+        e = c->tileOffset.reserve((size_t)numTiles + 1); if (e != cudaSuccess) return e;
+        e = c->tileCursor.reserve((size_t)numTiles + 2); if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(c->tileCount.p, 0, sizeof(uint32_t) * (numTiles + 1), c->stream); if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(c->tileCursor.p, 0, sizeof(uint32_t) * (numTiles + 2), c->stream); if (e != cudaSuccess) return e;
+        c->stageBegin(ST_SPLAT);
+        const unsigned pb = (count + 255) / 256;
+        splat_prepare_kernel<<<pb, 256, 0, c->stream>>>(sp, tg, c->records.p, c->photonList.p, devCount, c->splatPrep.p, c->tileCount.p);
+        size_t tempBytes = 0;
+        e = cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, c->tileCount.p, c->tileOffset.p, numTiles + 1, c->stream); if (e != cudaSuccess) return e;
+        e = c->sortTemp.reserve(tempBytes); if (e != cudaSuccess) return e;
+        e = cub::DeviceScan::ExclusiveSum(c->sortTemp.p, tempBytes, c->tileCount.p, c->tileOffset.p, numTiles + 1, c->stream); if (e != cudaSuccess) return e;
+        uint32_t* summary = c->tileCursor.p + numTiles + 1;  // max photons per tile
+        tile_summary_kernel<<<32, 256, 0, c->stream>>>(c->tileCount.p, numTiles, summary);
+        c->launches += 4;
+        uint32_t totalEntries = 0, maxPerTile = 0;
+        e = cudaMemcpyAsync(&totalEntries, c->tileOffset.p + numTiles, 4, cudaMemcpyDeviceToHost, c->stream); if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(&maxPerTile, summary, 4, cudaMemcpyDeviceToHost, c->stream); if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) return e;
+        if (totalEntries == 0) { c->stageEnd(ST_SPLAT); return cudaSuccess; }
+        if ((uint64_t)totalEntries <= (uint64_t)g_splatMaxEntries) {
+            e = c->tileList.reserve(totalEntries); if (e != cudaSuccess) return e;
+            splat_fill_kernel<<<pb, 256, 0, c->stream>>>(sp, tg, c->splatPrep.p, devCount, c->tileOffset.p, c->tileCursor.p, c->tileList.p);
+            const unsigned chunks = (maxPerTile + SPLAT_CHUNK - 1) / SPLAT_CHUNK;
+            dim3 grid(tg.nx, tg.ny, chunks);
+            splat_tile_kernel<<<grid, 256, 0, c->stream>>>(sp, tg, c->gbuf.p, c->gprim.p, c->splatPrep.p, c->tileOffset.p, c->tileList.p,
+                                                           c->accPhoton.p, chunks > 1 ? 1 : 0, c->devStats.p);
+            c->stageEnd(ST_SPLAT);
+            c->launches += 2;
+            return cudaGetLastError();
+        }
+        // footprints so large that the tile lists would not fit: fall through to the scatter kernel
+    }
+    const int G = g_splatGroup > 0 ? g_splatGroup : 32;
+    const uint64_t threadsWanted = (uint64_t)count * (uint64_t)G;
+    uint64_t blocks = (threadsWanted + 255) / 256;
+    const uint64_t maxBlocks = 148ull * 8ull * 8ull;
     if (blocks > maxBlocks) blocks = maxBlocks;
     c->stageBegin(ST_SPLAT);
-    splat_kernel<<<blocks, 256, 0, c->stream>>>(sp, c->gbuf.p, c->gprim.p, c->records.p, c->photonList.p, devCount,
-                                                c->accPhoton.p, c->devStats.p);
+    if (G == 32) splat_kernel<32><<<(unsigned)blocks, 256, 0, c->stream>>>(sp, c->gbuf.p, c->gprim.p, c->records.p, c->photonList.p, devCount, c->accPhoton.p, c->devStats.p);
+    else if (G == 8) splat_kernel<8><<<(unsigned)blocks, 256, 0, c->stream>>>(sp, c->gbuf.p, c->gprim.p, c->records.p, c->photonList.p, devCount, c->accPhoton.p, c->devStats.p);
+    else splat_kernel<1><<<(unsigned)blocks, 256, 0, c->stream>>>(sp, c->gbuf.p, c->gprim.p, c->records.p, c->photonList.p, devCount, c->accPhoton.p, c->devStats.p);
     c->stageEnd(ST_SPLAT);
     c->launches++;
     return cudaGetLastError();
