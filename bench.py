@@ -189,6 +189,9 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     lib = capi.load_library()
 
+    for kv in args.opt:  # process-wide tuning options (some must precede the BVH build)
+        name, value = kv.split("=")
+        capi.check(lib, lib.evplp_set_option(None, name.encode(), int(value)), "set_option")
     hs = HA.HostScene.generate(SCENE, SEED, DETAIL, RES_X / RES_Y)
     tech = HA.Technique(hs, PHOTONFAM, RES_X, RES_Y, device=local_rank, rank=rank, world_size=world)
     h = tech.device_handle()
@@ -196,9 +199,6 @@ def run_gpu(args):
     def ck(rc, what):
         capi.check(lib, rc, what)
 
-    for kv in args.opt:
-        name, value = kv.split("=")
-        ck(lib.evplp_set_option(h, name.encode(), int(value)), "set_option")
 
     def barrier():
         ck(lib.evplp_synchronize(h), "sync")

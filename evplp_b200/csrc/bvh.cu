@@ -196,7 +196,7 @@ __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint
                                 const int32_t* __restrict__ left, const int32_t* __restrict__ right,
                                 const int32_t* __restrict__ rangeFirst, const int32_t* __restrict__ rangeLast,
                                 const float* __restrict__ nodeBounds, const float* __restrict__ primLo,
-                                const float* __restrict__ primHi, const uint32_t* __restrict__ sorted, float pad,
+                                const float* __restrict__ primHi, const uint32_t* __restrict__ sorted, float pad, int leafMax,
                                 WideNode* __restrict__ nodes) {
     // counters: [0] = number of wide nodes allocated, [1 + (level&1)] = items in queueIn, [1 + (~level&1)] = out count
     const uint32_t numIn = counters[1 + (level & 1)];
@@ -214,7 +214,7 @@ __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint
         for (int k = 0; k < nc; k++) {
             int c = cand[k];
             if (c < 0) continue;
-            if (rangeLast[c] - rangeFirst[c] + 1 <= BVH_LEAF_MAX) continue;
+            if (rangeLast[c] - rangeFirst[c] + 1 <= leafMax) continue;
             float a = half_area(nodeBounds + 6 * (size_t)c);
             if (a > bestArea) { bestArea = a; best = k; }
         }
@@ -241,7 +241,7 @@ __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint
             nd.child[k] = bvh_make_leaf((uint32_t)(~c), 1u);
         } else {
             int cnt = rangeLast[c] - rangeFirst[c] + 1;
-            if (cnt <= BVH_LEAF_MAX) {
+            if (cnt <= leafMax) {
                 nd.child[k] = bvh_make_leaf((uint32_t)rangeFirst[c], (uint32_t)cnt);
             } else {
                 uint32_t idx = atomicAdd(&countersOut[0], 1u);
@@ -273,6 +273,8 @@ __global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const 
     nodes[0] = nd;
 }
 
+extern int g_bvhLeafMax;  // capi.cu: triangles per leaf child (1..8)
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (err) *err = std::string(#x) + ": " + cudaGetErrorString(e_); return e_; } } while (0)
 
 cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
@@ -293,6 +295,11 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     CK(c->sceneBoundsEnc.reserve(6));
     CK(c->queueA.reserve(2 * (size_t)(nInt + 1))); CK(c->queueB.reserve(2 * (size_t)(nInt + 1)));
     CK(c->counters.reserve(4));
+
+    size_t tempBytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, c->codes.p, c->codesSorted.p, c->primIds.p, c->primIdsSorted.p, n, 0, 63, st));
+    CK(c->sortTemp.reserve(tempBytes));
+    c->stageBegin(ST_BVH);  // device time of the build proper (allocations above are setup)
 
     const int TB = 256;
     const int gridN = (n + TB - 1) / TB;
@@ -316,15 +323,12 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     morton_kernel<<<gridN, TB, 0, st>>>(c->primLo.p, c->primHi.p, n, sb, c->codes.p, c->primIds.p);
     c->launches++;
     // 3 sort (stable LSD radix sort over the 63 used bits)
-    size_t tempBytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, c->codes.p, c->codesSorted.p, c->primIds.p, c->primIdsSorted.p, n, 0, 63, st));
-    CK(c->sortTemp.reserve(tempBytes));
     CK(cub::DeviceRadixSort::SortPairs(c->sortTemp.p, tempBytes, c->codes.p, c->codesSorted.p, c->primIds.p, c->primIdsSorted.p, n, 0, 63, st));
     c->launches += 9;  // histogram + onesweep passes (CUB-internal; counted approximately)
     // 4 leaf records
     leaf_records_kernel<<<gridN, TB, 0, st>>>(c->triVerts.p, c->primIdsSorted.p, n, c->triLeaf.p);
     c->launches++;
-    if (n <= BVH_LEAF_MAX) {
+    if (n <= g_bvhLeafMax) {
         tiny_root_kernel<<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->nodes.p);
         c->launches++;
         CK(cudaStreamSynchronize(st));
@@ -356,7 +360,7 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
         collapse_kernel<<<(numIn + 127) / 128, 128, 0, st>>>(qin, c->counters.p, level, qout, c->counters.p, c->left.p,
                                                             c->right.p, c->rangeFirst.p, c->rangeLast.p, c->nodeBounds.p,
                                                             c->primLo.p, c->primHi.p, c->primIdsSorted.p, c->boxPad,
-                                                            c->nodes.p);
+                                                            g_bvhLeafMax, c->nodes.p);
         c->launches++;
         uint32_t cnt[3];
         CK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));

@@ -13,6 +13,7 @@ namespace evplp {
 int g_gatherChunks = 0;
 int g_gatherMinBlocks = 3;
 int g_splatGroup = 0;
+int g_bvhLeafMax = BVH_LEAF_MAX;
 int g_splatMode = 0;
 int g_splatMaxEntries = 256 * 1024 * 1024;
 }
@@ -213,7 +214,6 @@ int evplp_build_bvh(evplp_handle c) {
     NEED(c != nullptr, "evplp_build_bvh: NULL handle");
     NEED(c->sceneLoaded, "evplp_build_bvh: no scene uploaded");
     CU(cudaSetDevice(c->device));
-    c->stageBegin(ST_BVH);
     std::string err;
     cudaError_t e = build_bvh_device(c, &err);
     c->stageEnd(ST_BVH);
@@ -433,7 +433,7 @@ int evplp_download_bvh(evplp_handle c, uint64_t* mortonCodes, uint32_t* sortedPr
     const size_t n = c->numPrims, ni = n > 1 ? n - 1 : 0;
     if (mortonCodes && n) CU(cudaMemcpyAsync(mortonCodes, c->codesSorted.p, 8 * n, cudaMemcpyDeviceToHost, c->stream));
     if (sortedPrimIds && n) CU(cudaMemcpyAsync(sortedPrimIds, c->primIdsSorted.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
-    const bool haveTopo = (int)n > BVH_LEAF_MAX;  // tiny scenes skip the radix tree
+    const bool haveTopo = (int)n > evplp::g_bvhLeafMax;  // tiny scenes skip the radix tree
     if (ni && !haveTopo && (left || right || parent || nodeBounds))
         return fail(EVPLP_ERR_INVALID, "evplp_download_bvh: scenes with <= BVH_LEAF_MAX triangles have no radix tree");
     if (left && ni) CU(cudaMemcpyAsync(left, c->left.p, 4 * ni, cudaMemcpyDeviceToHost, c->stream));
@@ -592,9 +592,11 @@ int evplp_event_elapsed_ms(evplp_handle c, int slotA, int slotB, float* ms) {
 }
 
 int evplp_set_option(evplp_handle c, const char* name, int value) {
-    NEED(c != nullptr && name != nullptr, "evplp_set_option: NULL argument");
+    (void)c;  // options are process-wide; the handle may be NULL (e.g. bvh_leaf_max must be set before evplp_build_bvh)
+    NEED(name != nullptr, "evplp_set_option: NULL name");
     if (strcmp(name, "gather_chunks") == 0) { evplp::g_gatherChunks = value; return EVPLP_OK; }
     if (strcmp(name, "gather_min_blocks") == 0) { evplp::g_gatherMinBlocks = value; return EVPLP_OK; }
+    if (strcmp(name, "bvh_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "bvh_leaf_max must be 1..8"); evplp::g_bvhLeafMax = value; return EVPLP_OK; }
     if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }
     if (strcmp(name, "splat_mode") == 0) { evplp::g_splatMode = value; return EVPLP_OK; }
     if (strcmp(name, "splat_max_entries") == 0) { evplp::g_splatMaxEntries = value; return EVPLP_OK; }

@@ -22,7 +22,7 @@
 namespace evplp {
 
 constexpr int BVH_WIDTH = 4;
-constexpr int BVH_LEAF_MAX = 4;             // triangles per leaf child
+constexpr int BVH_LEAF_MAX = 2;             // default triangles per leaf child (tunable: bvh_leaf_max)
 constexpr uint32_t BVH_EMPTY = 0x7fffffffu;
 constexpr uint32_t BVH_LEAF_BIT = 0x80000000u;
 constexpr int BVH_STACK = 96;

@@ -894,7 +894,7 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         chunks = (unsigned)g_gatherChunks;
     } else {
         const unsigned blocks = grid.x * grid.y;
-        const unsigned want = 148u * 4u;
+        const unsigned want = 148u * 3u * 6u;  // ~6 waves of resident blocks, so the tail wave stays short
         if (blocks < want) chunks = (want + blocks - 1) / blocks;
         const unsigned maxChunks = (count + 4 * GATHER_BATCH - 1) / (4 * GATHER_BATCH);
         if (chunks > maxChunks) chunks = maxChunks ? maxChunks : 1;

@@ -173,7 +173,7 @@ def test_vpl_gather_all_mis_modes(rig, mis):
     vpl5, _, _ = rig.dev.download_accum()
     rig.dev.set_option("gather_chunks", 0)
     a, b = vpl5.astype(np.float64), eacc.astype(np.float64)
-    assert np.max(np.abs(a - b) / (np.abs(b) + 2 ** 12)) < 1e-5
+    assert (np.abs(a - b) <= 6 + 1e-5 * np.abs(b)).all()  # 1e-5 relative + a few Q31.32 quanta (one rounding per chunk)
 
 
 def test_vpl_gather_accumulates_and_tiles(rig):
