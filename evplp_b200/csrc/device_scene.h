@@ -103,91 +103,6 @@ __device__ __forceinline__ bool tri_test(V3 org, V3 dir, float tmin, float tmax,
 
 __device__ __forceinline__ V3 ld3(const float4& v) { return v3(v.x, v.y, v.z); }
 
-// Closest hit, one ray per thread, private stack.
-__device__ inline RayHit trace_closest(const DevScene& sc, V3 org, V3 dir, float tmin, float tmax, int* overflow) {
-    RayHit best;
-    best.prim = -1; best.t = 0.f; best.beta = 0.f; best.gamma = 0.f; best.n = v3s(0.f); best.mat = 0;
-    if (sc.numNodes == 0) return best;
-    float bestT = tmax;
-    const RaySlab slab = make_slab(org, dir);
-    uint32_t stack[BVH_STACK];
-    int sp = 0;
-    uint32_t cur = 0;  // root node
-    while (true) {
-        if (cur & BVH_LEAF_BIT) {
-            const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
-            for (uint32_t k = 0; k < count; k++) {
-                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
-                float t, be, ga;
-                if (tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) {
-                    const int prim = __float_as_int(a.w);
-                    if (best.prim < 0 ? (t < bestT) : (t < bestT || (t == bestT && prim < best.prim))) {
-                        best.prim = prim; best.t = t; best.beta = be; best.gamma = ga; best.n = ld3(d);
-                        best.mat = __float_as_int(b.w);
-                        bestT = t;
-                    }
-                }
-            }
-        } else {
-            const WideNode& nd = sc.nodes[cur];
-            float tn[BVH_WIDTH];
-            uint32_t ch[BVH_WIDTH];
-            int nh = 0;
-#pragma unroll
-            for (int c = 0; c < BVH_WIDTH; c++) {
-                float t;
-                const uint32_t cd = nd.child[c];
-                if (cd != BVH_EMPTY && slab_test(slab, nd, c, tmin, bestT, &t)) {
-                    // insertion sort by entry distance, nearest last (popped first)
-                    int j = nh++;
-                    while (j > 0 && tn[j - 1] < t) { tn[j] = tn[j - 1]; ch[j] = ch[j - 1]; j--; }
-                    tn[j] = t; ch[j] = cd;
-                }
-            }
-            for (int j = 0; j < nh; j++) {
-                if (sp < BVH_STACK) stack[sp++] = ch[j]; else *overflow = 1;
-            }
-        }
-        if (sp == 0) break;
-        cur = stack[--sp];
-    }
-    return best;
-}
-
-// Any hit, one ray per thread, private stack.
-__device__ inline bool trace_any(const DevScene& sc, V3 org, V3 dir, float tmin, float tmax, int* overflow) {
-    if (sc.numNodes == 0) return false;
-    const RaySlab slab = make_slab(org, dir);
-    uint32_t stack[BVH_STACK];
-    int sp = 0;
-    uint32_t cur = 0;
-    while (true) {
-        if (cur & BVH_LEAF_BIT) {
-            const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
-            for (uint32_t k = 0; k < count; k++) {
-                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
-                float t, be, ga;
-                if (tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) return true;
-            }
-        } else {
-            const WideNode& nd = sc.nodes[cur];
-#pragma unroll
-            for (int c = 0; c < BVH_WIDTH; c++) {
-                float t;
-                const uint32_t cd = nd.child[c];
-                if (cd != BVH_EMPTY && slab_test(slab, nd, c, tmin, tmax, &t)) {
-                    if (sp < BVH_STACK) stack[sp++] = cd; else *overflow = 1;
-                }
-            }
-        }
-        if (sp == 0) break;
-        cur = stack[--sp];
-    }
-    return false;
-}
-
 // Any hit for a whole warp at once: the 32 rays walk the tree together with ONE shared
 // stack, so every node / triangle is fetched once per warp (uniform address -> broadcast)
 // and there is no divergence.  Rays of the gather are coherent (neighbouring pixels, same
@@ -224,8 +139,6 @@ __device__ __forceinline__ bool slab4(const RaySlab& s, float lx, float ly, floa
     const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
     return tn <= tf;
 }
-
-static_assert(BVH_WIDTH == 4, "trace_any_warp is written for 4-wide nodes");
 
 // ---- warp-cooperative any-hit traversal -------------------------------------------------------
 // Shared-memory stack addressed by a 32-bit shared-window byte address kept in a register.
@@ -265,6 +178,117 @@ __device__ __forceinline__ bool slab_masked(const RaySlabM& s, float lx, float l
     return tn <= tf;
 }
 
+// entry distance of a child for the sign-masked slab test (+inf when the ray misses the box)
+__device__ __forceinline__ float slab_entry_masked(const RaySlabM& s, float lx, float ly, float lz, float hx, float hy, float hz,
+                                                   float tmin, float tmax) {
+    const float nx = __fmaf_rn(lx, s.ax, __fmaf_rn(hx, s.bx, s.ox)), fx = __fmaf_rn(lx, s.bx, __fmaf_rn(hx, s.ax, s.ox));
+    const float ny = __fmaf_rn(ly, s.ay, __fmaf_rn(hy, s.by, s.oy)), fy = __fmaf_rn(ly, s.by, __fmaf_rn(hy, s.ay, s.oy));
+    const float nz = __fmaf_rn(lz, s.az, __fmaf_rn(hz, s.bz, s.oz)), fz = __fmaf_rn(lz, s.bz, __fmaf_rn(hz, s.az, s.oz));
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float tf = fminf(fminf(fx, fy), fminf(fz, tmax));
+    return tn <= tf ? tn : INFINITY;
+}
+
+// order (ta, ca), (tb, cb) so that ta >= tb
+__device__ __forceinline__ void cswap_desc(float& ta, uint32_t& ca, float& tb, uint32_t& cb) {
+    const bool sw = ta < tb;
+    const float hi = fmaxf(ta, tb), lo = fminf(ta, tb);
+    const uint32_t c_hi = sw ? cb : ca, c_lo = sw ? ca : cb;
+    ta = hi; tb = lo; ca = c_hi; cb = c_lo;
+}
+
+// Closest hit, one ray per thread, private stack.  Children are visited front to back (sorting
+// network on the entry distances); popped entries that start beyond the current best hit are skipped.
+__device__ inline RayHit trace_closest(const DevScene& sc, V3 org, V3 dir, float tmin, float tmax, int* overflow) {
+    RayHit best;
+    best.prim = -1; best.t = 0.f; best.beta = 0.f; best.gamma = 0.f; best.n = v3s(0.f); best.mat = 0;
+    if (sc.numNodes == 0) return best;
+    float bestT = tmax;
+    const RaySlabM slab = make_slab_masked(org, dir);
+    uint32_t stack[BVH_STACK];
+    float stackT[BVH_STACK];
+    int sp = 0;
+    uint32_t cur = 0;  // root node
+    while (true) {
+        if (cur & BVH_LEAF_BIT) {
+            const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
+            for (uint32_t k = 0; k < count; k++) {
+                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+                float t, be, ga;
+                if (tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) {
+                    const int prim = __float_as_int(a.w);
+                    if (best.prim < 0 ? (t < bestT) : (t < bestT || (t == bestT && prim < best.prim))) {
+                        best.prim = prim; best.t = t; best.beta = be; best.gamma = ga; best.n = ld3(d);
+                        best.mat = __float_as_int(b.w);
+                        bestT = t;
+                    }
+                }
+            }
+            cur = BVH_EMPTY;
+        } else {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
+            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+            const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+            float t0 = slab_entry_masked(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, bestT);
+            float t1 = slab_entry_masked(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, bestT);
+            float t2 = slab_entry_masked(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, bestT);
+            float t3 = slab_entry_masked(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, bestT);
+            uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+            cswap_desc(t0, c0, t1, c1); cswap_desc(t2, c2, t3, c3); cswap_desc(t0, c0, t2, c2);
+            cswap_desc(t1, c1, t3, c3); cswap_desc(t1, c1, t2, c2);
+            // (t0 >= t1 >= t2 >= t3; misses are +inf and sort to the front)
+            if (sp + 3 > BVH_STACK) { *overflow = 1; break; }
+            if (t0 < INFINITY) { stack[sp] = c0; stackT[sp] = t0; sp++; }
+            if (t1 < INFINITY) { stack[sp] = c1; stackT[sp] = t1; sp++; }
+            if (t2 < INFINITY) { stack[sp] = c2; stackT[sp] = t2; sp++; }
+            cur = t3 < INFINITY ? c3 : BVH_EMPTY;  // nearest child continues without a stack round trip
+        }
+        while (cur == BVH_EMPTY) {
+            if (sp == 0) return best;
+            --sp;
+            if (stackT[sp] <= bestT) cur = stack[sp];  // entries that begin beyond the best hit cannot improve it (ties kept)
+        }
+    }
+    return best;
+}
+
+// Any hit, one ray per thread, private stack.
+__device__ inline bool trace_any(const DevScene& sc, V3 org, V3 dir, float tmin, float tmax, int* overflow) {
+    if (sc.numNodes == 0) return false;
+    const RaySlab slab = make_slab(org, dir);
+    uint32_t stack[BVH_STACK];
+    int sp = 0;
+    uint32_t cur = 0;
+    while (true) {
+        if (cur & BVH_LEAF_BIT) {
+            const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
+            for (uint32_t k = 0; k < count; k++) {
+                const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+                float t, be, ga;
+                if (tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga)) return true;
+            }
+        } else {
+            const WideNode& nd = sc.nodes[cur];
+#pragma unroll
+            for (int c = 0; c < BVH_WIDTH; c++) {
+                float t;
+                const uint32_t cd = nd.child[c];
+                if (cd != BVH_EMPTY && slab_test(slab, nd, c, tmin, tmax, &t)) {
+                    if (sp < BVH_STACK) stack[sp++] = cd; else *overflow = 1;
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return false;
+}
+
+static_assert(BVH_WIDTH == 4, "trace_any_warp is written for 4-wide nodes");
+
 static_assert(BVH_WIDTH == 4, "the warp traversal is written for 4-wide nodes");
 
 // Any hit for a whole warp at once: the 32 rays walk the tree together with ONE shared
@@ -299,6 +323,7 @@ __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V
             }
             open = open && !hit;
             if (!__any_sync(full, open)) break;
+            cur = BVH_EMPTY;
         } else {
             const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
             const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
@@ -308,18 +333,22 @@ __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V
             const bool h1 = slab_masked(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, tmax);
             const bool h2 = slab_masked(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, tmax);
             const bool h3 = slab_masked(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, tmax);
-            // warp-uniform from here on: every lane performs the same pushes (identical values)
+            // warp-uniform from here on: every lane performs the same pushes (identical values);
+            // the last entered child continues in a register (no stack round trip on the critical path)
             const bool p0 = __any_sync(full, h0 & open), p1 = __any_sync(full, h1 & open);
             const bool p2 = __any_sync(full, h2 & open), p3 = __any_sync(full, h3 & open);
-            if (sp + 16u > stackBase + 4u * BVH_STACK) { *overflow = 1; break; }
-            if (p0) { st_shared_u32(sp, ch.x); sp += 4u; }
-            if (p1) { st_shared_u32(sp, ch.y); sp += 4u; }
-            if (p2) { st_shared_u32(sp, ch.z); sp += 4u; }
-            if (p3) { st_shared_u32(sp, ch.w); sp += 4u; }
+            if (sp + 12u > stackBase + 4u * BVH_STACK) { *overflow = 1; break; }
+            cur = BVH_EMPTY;
+            if (p0) cur = ch.x;
+            if (p1) { if (cur != BVH_EMPTY) { st_shared_u32(sp, cur); sp += 4u; } cur = ch.y; }
+            if (p2) { if (cur != BVH_EMPTY) { st_shared_u32(sp, cur); sp += 4u; } cur = ch.z; }
+            if (p3) { if (cur != BVH_EMPTY) { st_shared_u32(sp, cur); sp += 4u; } cur = ch.w; }
         }
-        if (sp == stackBase) break;
-        sp -= 4u;
-        cur = ld_shared_u32(sp);
+        if (cur == BVH_EMPTY) {
+            if (sp == stackBase) break;
+            sp -= 4u;
+            cur = ld_shared_u32(sp);
+        }
     }
     return active && !open;
 }
