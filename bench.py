@@ -321,8 +321,9 @@ def run_gpu(args):
                          "frac": ach / fp32_peak, "traffic": None,
                          "note": f"{FLOP_PER_PAIR:.0f} algorithmic FP32 flop per pair (SURVEY 8d) x pairs / gather kernel time; peak = "
                                  f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz ({how} clock); the kernel is shadow-ray traversal bound, "
-                                 "not HBM or tensor bound"},
-            "roofline_splat": {"kernel": "splat_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
+                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v4_ncu_full_summary.txt: 67 % of peak "
+                                 "instruction issue, ALU pipe 42 %, FMA pipe 32 %, DRAM 0.01 %)"},
+            "roofline_splat": {"kernel": "splat_prepare + splat_fill + splat_tile_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": None,
                                "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}"},
             "clocks": clk, "gpu_launches": int(l1 - l0),
