@@ -18,3 +18,20 @@ def test_two_gpus_equal_one_gpu_bit_for_bit(lib):
     sys.stdout.write(r.stdout[-2000:])
     assert r.returncode == 0, r.stderr[-3000:]
     assert r.stdout.count("True") == 3
+
+
+def test_evplp_reduce_with_real_nccl_communicators(lib, tmp_path):
+    """The C-ABI reduce entry point with raw ncclComm_t handles (one process, two GPUs)."""
+    if lib.evplp_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = str(tmp_path / "nccl_reduce_test")
+    src = os.path.join(ROOT, "tests", "hostsim", "nccl_reduce_test.cpp")
+    libdir = os.path.join(ROOT, "evplp_b200", "lib")
+    cc = subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", src, "-o", exe, "-I/usr/local/cuda/include", f"-L{libdir}", "-levplp_b200",
+                         "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                        capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("cannot build the NCCL test program here: " + cc.stderr[-300:])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK" in r.stdout or "SKIP" in r.stdout
