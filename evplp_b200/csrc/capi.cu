@@ -11,6 +11,7 @@ using namespace evplp;
 
 namespace evplp {
 int g_gatherChunks = 0;
+int g_bandStride = 0, g_bandOffset = 0;
 int g_gatherMinBlocks = 3;
 int g_splatGroup = 0;
 int g_bvhLeafMax = BVH_LEAF_MAX;
@@ -534,12 +535,10 @@ int evplp_stats(evplp_handle c, EvplpStats* stats) {
     // emitted counts of the current record window
     stats->emittedVpls = 0; stats->emittedPhotons = 0;
     if (c->numRecords) {
-        std::vector<EvplpRecord> tmp(c->numRecords);
-        CU(cudaMemcpy(tmp.data(), c->records.p, c->numRecords * sizeof(EvplpRecord), cudaMemcpyDeviceToHost));
-        for (const EvplpRecord& r : tmp) {
-            if (r.flags & EVPLP_FLAG_USABLE_VPL) stats->emittedVpls++;
-            if (r.flags & EVPLP_FLAG_USABLE_PHOTON) stats->emittedPhotons++;
-        }
+        unsigned long long counts[2] = {0, 0};
+        CU(launch_count_flags(c, counts));
+        stats->emittedVpls = counts[0];
+        stats->emittedPhotons = counts[1];
     }
     if (ds.stackOverflow) return fail(EVPLP_ERR_CUDA, "BVH traversal stack overflow");
     return EVPLP_OK;
@@ -595,6 +594,8 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
     (void)c;  // options are process-wide; the handle may be NULL (e.g. bvh_leaf_max must be set before evplp_build_bvh)
     NEED(name != nullptr, "evplp_set_option: NULL name");
     if (strcmp(name, "gather_chunks") == 0) { evplp::g_gatherChunks = value; return EVPLP_OK; }
+    if (strcmp(name, "gather_band_stride") == 0) { NEED(value >= 0, "gather_band_stride must be >= 0"); evplp::g_bandStride = value; return EVPLP_OK; }
+    if (strcmp(name, "gather_band_offset") == 0) { NEED(value >= 0, "gather_band_offset must be >= 0"); evplp::g_bandOffset = value; return EVPLP_OK; }
     if (strcmp(name, "gather_min_blocks") == 0) { evplp::g_gatherMinBlocks = value; return EVPLP_OK; }
     if (strcmp(name, "bvh_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "bvh_leaf_max must be 1..8"); evplp::g_bvhLeafMax = value; return EVPLP_OK; }
     if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }

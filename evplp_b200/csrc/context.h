@@ -118,6 +118,7 @@ cudaError_t launch_resolve(EvplpContext* c, float vplScale, float photonScale, f
 cudaError_t launch_trace_rays(EvplpContext* c, const float* devRays, uint64_t n, int anyHit, int32_t* devPrim, float* devT);
 cudaError_t launch_debug_uniforms(EvplpContext* c, uint32_t seed, uint32_t n, float* devOut);
 cudaError_t launch_debug_curand(EvplpContext* c, uint32_t seed, uint32_t subsequence, uint32_t n, float* devOut);
+cudaError_t launch_count_flags(EvplpContext* c, unsigned long long counts[2]);
 cudaError_t launch_debug_math(EvplpContext* c, int op, const float* x, const float* y, uint32_t n, float* out);
 // host_xorwow.cpp
 void xorwow_compose_skip(uint32_t subsequence, uint32_t* out800);

@@ -231,6 +231,7 @@ struct GatherParams {
     unsigned numChunks;  // VPL list split over gridDim.z
     float vslRadius, vslInvPiRadius2;
     unsigned numLightPaths, numVplLightPaths, B1;
+    int bandStride, bandOffset;  // this launch owns the 16-row bands b = bandOffset (mod bandStride) of the tile (multi-GPU interleave)
 };
 
 template <int MINB>
@@ -245,7 +246,7 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* batch = batchAll[warp];
     const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = gp.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const int y = gp.y0 + (blockIdx.y * gp.bandStride + gp.bandOffset) * 16 + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = x < gp.x1 && y < gp.y1;
     const size_t n = (size_t)gp.W * gp.H;
     const size_t i = inside ? (size_t)y * gp.W + x : 0;
@@ -450,7 +451,7 @@ gather_vsl_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ ski
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = gp.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const int y = gp.y0 + (blockIdx.y * gp.bandStride + gp.bandOffset) * 16 + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = x < gp.x1 && y < gp.y1;
     const size_t n = (size_t)gp.W * gp.H;
     const size_t i = inside ? (size_t)y * gp.W + x : 0;
@@ -491,7 +492,7 @@ gather_lvc_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ ski
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = gp.y0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const int y = gp.y0 + (blockIdx.y * gp.bandStride + gp.bandOffset) * 16 + (warp >> 1) * 4 + (lane >> 3);
     if (!(x < gp.x1 && y < gp.y1)) return;
     const size_t n = (size_t)gp.W * gp.H;
     const size_t i = (size_t)y * gp.W + x;
@@ -834,6 +835,13 @@ cudaError_t launch_light_trace(EvplpContext* c, uint32_t rngSeed, uint32_t first
     return cudaGetLastError();
 }
 
+extern int g_gatherChunks;     // capi.cu (0 = automatic)
+extern int g_bandStride, g_bandOffset;  // capi.cu: 16-row band interleave of the gather (multi-GPU image partition)
+extern int g_splatGroup;       // capi.cu: lanes per photon in the scatter splat (0 = 32; 1 / 8 / 32)
+extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatter splat
+extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
+extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
+
 static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
     const EvplpParams& P = c->params;
     GatherParams g;
@@ -845,21 +853,22 @@ static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
     g.numChunks = 1;
     g.vslRadius = P.vslRadius; g.vslInvPiRadius2 = P.vslInvPiRadius2;
     g.numLightPaths = P.numLightPaths; g.numVplLightPaths = P.numVplLightPaths; g.B1 = P.numPhotonsPerLightPath;
+    g.bandStride = g_bandStride > 0 ? g_bandStride : 1;
+    g.bandOffset = g_bandStride > 0 ? g_bandOffset : 0;
     return g;
 }
-
-extern int g_gatherChunks;     // capi.cu (0 = automatic)
-extern int g_splatGroup;       // capi.cu: lanes per photon in the scatter splat (0 = 32; 1 / 8 / 32)
-extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatter splat
-extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
-extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
 
 cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     const EvplpParams& P = c->params;
     GatherParams g = gather_params(c, t);
     const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
     if (tw <= 0 || th <= 0) return cudaSuccess;
-    dim3 grid((tw + 15) / 16, (th + 15) / 16, 1);
+    const int bands = (th + 15) / 16;
+    if (g.bandOffset >= bands) return cudaSuccess;  // this rank owns no band of the tile
+    const int ownBands = (bands - g.bandOffset + g.bandStride - 1) / g.bandStride;
+    uint64_t ownRows = 0;
+    for (int b = g.bandOffset; b < bands; b += g.bandStride) ownRows += (uint64_t)((b + 1) * 16 <= th ? 16 : th - b * 16);
+    dim3 grid((tw + 15) / 16, ownBands, 1);
     cudaError_t e;
     if (mode == EVPLP_GATHER_LVC) {
         c->stageBegin(ST_GATHER);
@@ -879,7 +888,7 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     if (e != cudaSuccess) return e;
     e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return e;
-    c->stats.gatherPairs += (uint64_t)count * (uint64_t)tw * th;
+    c->stats.gatherPairs += (uint64_t)count * (uint64_t)tw * ownRows;
     if (mode == EVPLP_GATHER_VSL) {
         c->stageBegin(ST_GATHER);
         gather_vsl_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->skipMatrix.p, c->gbuf.p, c->records.p,
@@ -1008,6 +1017,31 @@ cudaError_t launch_resolve(EvplpContext* c, float vplScale, float photonScale, f
     c->stageEnd(ST_RESOLVE);
     c->launches++;
     return cudaGetLastError();
+}
+
+// emitted VPL / photon counts of the current record window (evplp_stats)
+__global__ void count_flags_kernel(const EvplpRecord* __restrict__ records, uint64_t n, unsigned long long* out) {
+    unsigned v = 0, p = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t f = records[i].flags;
+        v += (f & EVPLP_FLAG_USABLE_VPL) ? 1u : 0u;
+        p += (f & EVPLP_FLAG_USABLE_PHOTON) ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
+    if ((threadIdx.x & 31) == 0) { if (v) atomicAdd(&out[0], (unsigned long long)v); if (p) atomicAdd(&out[1], (unsigned long long)p); }
+}
+
+cudaError_t launch_count_flags(EvplpContext* c, unsigned long long counts[2]) {
+    unsigned long long* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, 16);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(d, 0, 16, c->stream);
+    count_flags_kernel<<<148 * 8, 256, 0, c->stream>>>(c->records.p, c->numRecords, d);
+    c->launches++;
+    e = cudaMemcpyAsync(counts, d, 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    return e;
 }
 
 // ------------------------------------------------------------------ debug taps ----------

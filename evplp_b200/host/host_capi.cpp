@@ -86,13 +86,15 @@ int evplp_host_scene_info(void* s, float scalars[3], float camera[14]) {
 }
 
 // RtComPhoton / RtLvcComPhoton over a scene; `techniqueJson` is the text of the "photonfam" object.
-void* evplp_host_technique_create(void* s, const char* techniqueJson, int resX, int resY, int device, int lvc, int rank, int worldSize) {
+// partitionMode: 0 = iterations round-robin over the ranks, 1 = image bands + light-path ranges (RtComPhoton::EPartition)
+void* evplp_host_technique_create(void* s, const char* techniqueJson, int resX, int resY, int device, int lvc, int rank, int worldSize,
+                                  int partitionMode) {
     try {
         HostScene* hs = (HostScene*)s;
         auto* ht = new HostTechnique();
         ht->scene = hs->scene;
         ht->tech.reset(lvc ? new RtLvcComPhoton(device) : new RtComPhoton(device));
-        ht->tech->setPartition(rank, worldSize);
+        ht->tech->setPartition(rank, worldSize, partitionMode ? RtComPhoton::PartitionImage : RtComPhoton::PartitionIterations);
         ht->tech->setWriteOutputs(false);
         Vec2 res; res.x = (float)resX; res.y = (float)resY;
         ht->tech->parse(ht->scene, res, Json::parse(techniqueJson));

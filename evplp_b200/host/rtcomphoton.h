@@ -50,7 +50,11 @@ public:
     explicit RtComPhoton(int device = 0, int gatherMode = EVPLP_GATHER_VPL) : mDevice(device), mBaseGatherMode(gatherMode) {}
     ~RtComPhoton() override { destroy(); }
 
-    void setPartition(int rank, int worldSize) { mRank = rank; mWorldSize = worldSize; }
+    // Multi-GPU partition (new; the reference is single-GPU).  PartitionIterations: rank g renders the iterations
+    // k = g (mod N) end to end (progressive / accumulate runs).  PartitionImage: every rank renders every iteration but
+    // only its interleaved 16-row bands of the gather and its contiguous range of light paths of the splat (one heavy frame).
+    enum EPartition { PartitionIterations = 0, PartitionImage = 1 };
+    void setPartition(int rank, int worldSize, EPartition mode = PartitionIterations) { mRank = rank; mWorldSize = worldSize; mPartition = mode; }
     void setNcclComm(void* comm) { mNcclComm = comm; }
     void setWriteOutputs(bool w) { mWriteOutputs = w; }
 
@@ -146,6 +150,9 @@ public:
         mMainSampler.reset(new IndependentSampler(mRngOffset));
         mNumIterations = 0;
         check(evplp_clear_accum(mHandle), "evplp_clear_accum");
+        const bool imageMode = mPartition == PartitionImage && mWorldSize > 1;
+        check(evplp_set_option(mHandle, "gather_band_stride", imageMode ? mWorldSize : 0), "evplp_set_option");
+        check(evplp_set_option(mHandle, "gather_band_offset", imageMode ? mRank : 0), "evplp_set_option");
         mMasterWatch.reset();
         mPrevTiming = 0.f;
     }
@@ -160,7 +167,13 @@ public:
         check(evplp_vpl_gather(mHandle, nullptr, mode), "evplp_vpl_gather");
     }
     void runPhotonSplat() {                                                                             // :789-837
-        check(evplp_photon_splat(mHandle, 0, (uint64_t)mNumLightPaths * mNumPhotonsPerLightPath, nullptr), "evplp_photon_splat");
+        uint64_t firstPath = 0, numPaths = mNumLightPaths;
+        if (mPartition == PartitionImage && mWorldSize > 1) {  // this rank splats its contiguous range of light paths
+            firstPath = (uint64_t)mNumLightPaths * (uint64_t)mRank / (uint64_t)mWorldSize;
+            numPaths = (uint64_t)mNumLightPaths * (uint64_t)(mRank + 1) / (uint64_t)mWorldSize - firstPath;
+        }
+        check(evplp_photon_splat(mHandle, firstPath * mNumPhotonsPerLightPath, numPaths * mNumPhotonsPerLightPath, nullptr),
+              "evplp_photon_splat");
     }
     void runLightProgram() { check(evplp_light_pass(mHandle), "evplp_light_pass"); }                    // :839-855
     FloatImage runFinalProgram(float vplScale, float photonScale, float lightScale, bool gamma) {        // :756-787 + dumpImage :225-249
@@ -213,7 +226,8 @@ public:
             jitter.x = (2.0f * xi.x - 1.0f) * mInvResolution.x;
             jitter.y = (2.0f * xi.y - 1.0f) * mInvResolution.y;
         }
-        const bool mine = (mNumIterations % mWorldSize) == mRank;  // iteration partition over GPUs
+        const bool imageMode = mPartition == PartitionImage && mWorldSize > 1;
+        const bool mine = imageMode || (mNumIterations % mWorldSize) == mRank;  // iteration partition over GPUs
         if (mine) {
             pushParams(jitter, (uint32_t)mNumIterations + mRngOffset);
             if (mFrameMode == ClearEveryFrame) check(evplp_clear_accum(mHandle), "evplp_clear_accum");
@@ -221,7 +235,7 @@ public:
             if (mDoLightTracing) runOptixLightTracingProgram((uint32_t)mNumIterations + mRngOffset);
             if (mDoVplSplat) runOptixVplProgram();
             if (mDoPhotonSplat) runPhotonSplat();
-            if (mDoLightRender) runLightProgram();
+            if (mDoLightRender && (!imageMode || mRank == 0)) runLightProgram();
         }
         mNumIterations++;
         if (mNumIterations % 20 == 0 && mRank == 0) {
@@ -315,6 +329,7 @@ protected:
         if (rc != EVPLP_OK) throw std::runtime_error(std::string(what) + ": " + evplp_last_error());
     }
     int mDevice = 0, mBaseGatherMode = EVPLP_GATHER_VPL, mRank = 0, mWorldSize = 1;
+    EPartition mPartition = PartitionIterations;
     void* mNcclComm = nullptr;
     bool mWriteOutputs = true;
     evplp_handle mHandle = nullptr;

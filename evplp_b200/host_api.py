@@ -36,7 +36,7 @@ def load_host_library():
                                                  C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.evplp_host_scene_info.argtypes = [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.evplp_host_technique_create.restype = _P
-    lib.evplp_host_technique_create.argtypes = [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.evplp_host_technique_create.argtypes = [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.evplp_host_technique_handle.restype = _P
     lib.evplp_host_technique_handle.argtypes = [_P]
     lib.evplp_host_technique_iterate.argtypes = [_P]
@@ -146,11 +146,12 @@ class HostScene:
 class Technique:
     """RtComPhoton (or RtLvcComPhoton) of the C++ host library, stepped one iteration at a time."""
 
-    def __init__(self, host_scene, photonfam, res_x, res_y, device=0, lvc=False, rank=0, world_size=1):
+    def __init__(self, host_scene, photonfam, res_x, res_y, device=0, lvc=False, rank=0, world_size=1, image_partition=False):
         self.lib = load_host_library()
         self.W, self.H = res_x, res_y
         text = json.dumps(photonfam).encode()
-        self.h = self.lib.evplp_host_technique_create(host_scene.h, text, res_x, res_y, device, 1 if lvc else 0, rank, world_size)
+        self.h = self.lib.evplp_host_technique_create(host_scene.h, text, res_x, res_y, device, 1 if lvc else 0, rank, world_size,
+                                                      1 if image_partition else 0)
         if not self.h:
             _err(self.lib, "evplp_host_technique_create")
         self._scene = host_scene

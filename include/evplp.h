@@ -244,7 +244,11 @@ int evplp_event_record(evplp_handle h, int slot);
 int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
 /* Tuning knobs (no reference counterpart).  "gather_chunks": number of slices the VPL list is
  * split into across thread blocks (0 = automatic; 1 = every pixel sums its VPLs in record
- * order in one thread, which makes the gather bit-identical to the scalar oracle). */
+ * order in one thread, which makes the gather bit-identical to the scalar oracle).
+ * "gather_band_stride" / "gather_band_offset": the gather only renders the 16-row bands b = offset (mod stride) of its
+ * tile -- the interleaved image partition of a single heavy frame over N GPUs (stride = N, offset = rank).
+ * "bvh_leaf_max" (before evplp_build_bvh), "gather_min_blocks", "splat_mode" (0 tiled, 1 scatter), "splat_group",
+ * "splat_max_entries": kernel variants.  Options are process-wide; the handle may be NULL. */
 int evplp_set_option(evplp_handle h, const char* name, int value);
 
 #ifdef __cplusplus

@@ -21,9 +21,9 @@ FAM = {"rngOffset": 3, "numMaxIteration": -1, "timeLimitMs": -1.0, "frameMode": 
        "misMode": "geometryClamp", "DoProgressive": True, "AlphaProgressive": 0.7}
 
 
-def render(hs, device, rank, world):
+def render(hs, device, rank, world, image_partition=False):
     lib = capi.load_library()
-    t = HA.Technique(hs, FAM, W, H, device=device, rank=rank, world_size=world)
+    t = HA.Technique(hs, FAM, W, H, device=device, rank=rank, world_size=world, image_partition=image_partition)
     h = t.device_handle()
     capi.check(lib, lib.evplp_set_option(h, b"gather_chunks", 1), "opt")
     for _ in range(ITERS):
@@ -50,23 +50,25 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     hs = HA.HostScene.generate("livingroom", 2, 2, W / H)
-    t, h, lib = render(hs, local, rank, world)
-    ls = layers(lib, h, local)
-    for x in ls:
-        dist.all_reduce(x, op=dist.ReduceOp.SUM)
-    torch.cuda.synchronize()
     ok = True
-    if rank == 0:
-        t1, h1, _ = render(hs, local, 0, 1)
-        ref = layers(lib, h1, local)
-        for name, a, b in zip(("vpl", "photon", "light"), ls, ref):
-            same = bool(torch.equal(a, b))
-            print(f"layer {name}: N={world} reduce == 1-GPU: {same} (sum {int(a.sum())})")
-            ok &= same and (name == "light" or int(a.abs().sum()) > 0)  # the light may be outside the view
-        # evplp_reduce with a raw ncclComm is exercised through torch's communicator-free path only; the C ABI entry is
-        # covered by symbol tests (it needs an ncclComm_t that torch does not expose).
-        t1.close()
-    t.close()
+    ref = None
+    for image_partition in (False, True):
+        t, h, lib = render(hs, local, rank, world, image_partition)
+        ls = layers(lib, h, local)
+        for x in ls:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        if rank == 0:
+            if ref is None:
+                t1, h1, _ = render(hs, local, 0, 1)
+                ref = [x.clone() for x in layers(lib, h1, local)]
+                t1.close()
+            mode = "image bands + path ranges" if image_partition else "iterations round-robin"
+            for name, a, b in zip(("vpl", "photon", "light"), ls, ref):
+                same = bool(torch.equal(a, b))
+                print(f"[{mode}] layer {name}: N={world} reduce == 1-GPU: {same} (sum {int(a.sum())})")
+                ok &= same and (name == "light" or int(a.abs().sum()) > 0)  # the light may be outside the view
+        t.close()
     dist.destroy_process_group()
     if not ok:
         sys.exit(1)

@@ -17,7 +17,7 @@ def test_two_gpus_equal_one_gpu_bit_for_bit(lib):
                        capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-2000:])
     assert r.returncode == 0, r.stderr[-3000:]
-    assert r.stdout.count("True") == 3
+    assert r.stdout.count("True") == 6  # 3 layers x 2 partition modes
 
 
 def test_evplp_reduce_with_real_nccl_communicators(lib, tmp_path):
