@@ -722,12 +722,22 @@ __global__ void __launch_bounds__(256) splat_tile_kernel(SplatParams sp, TileGri
         for (uint32_t k = threadIdx.x; k < nb * SPLAT_PREP_F4; k += blockDim.x)
             batch[k] = __ldg(prep + (size_t)tileList[first + base + k / SPLAT_PREP_F4] * SPLAT_PREP_F4 + k % SPLAT_PREP_F4);
         __syncthreads();
-        for (uint32_t j = 0; j < nb; j++) {
-            const float4 p0 = batch[j * SPLAT_PREP_F4];
-            const V3 d = v3(p0.x, p0.y, p0.z) - sf.pos;
-            if (!valid || dot(d, d) > r2) continue;
-            const float4 p1 = batch[j * SPLAT_PREP_F4 + 1], p2 = batch[j * SPLAT_PREP_F4 + 2], p3 = batch[j * SPLAT_PREP_F4 + 3],
-                         p4 = batch[j * SPLAT_PREP_F4 + 4];
+        // phase 1: radius test of this texel against every staged photon -> 64-bit hit mask (cheap, uniform loop)
+        unsigned long long hits = 0ull;
+        if (valid) {
+            for (uint32_t j = 0; j < nb; j++) {
+                const float4 p0 = batch[j * SPLAT_PREP_F4];
+                const V3 d = v3(p0.x, p0.y, p0.z) - sf.pos;
+                if (!(dot(d, d) > r2)) hits |= 1ull << j;
+            }
+        }
+        // phase 2: every lane shades ITS OWN hits (ascending j), so a warp iterates max-hits-per-lane times instead of
+        // once per photon that any of its lanes touches
+        while (hits) {
+            const int j = __ffsll((long long)hits) - 1;
+            hits &= hits - 1ull;
+            const float4 p0 = batch[j * SPLAT_PREP_F4], p1 = batch[j * SPLAT_PREP_F4 + 1], p2 = batch[j * SPLAT_PREP_F4 + 2],
+                         p3 = batch[j * SPLAT_PREP_F4 + 3], p4 = batch[j * SPLAT_PREP_F4 + 4];
             SplatPhoton q;
             q.pos = v3(p0.x, p0.y, p0.z); q.live = __float_as_int(p0.w);
             q.w12 = v3(p1.x, p1.y, p1.z); q.weight = p1.w;

@@ -103,6 +103,8 @@ void* evplp_host_technique_create(void* s, const char* techniqueJson, int resX, 
     } catch (const std::exception& e) { g_hostErr = e.what(); return nullptr; }
 }
 
+void evplp_host_technique_set_max_paths_per_trace(void* t, uint64_t n) { ((HostTechnique*)t)->tech->setMaxPathsPerTrace(n); }
+
 void* evplp_host_technique_handle(void* t) { return ((HostTechnique*)t)->tech->handle(); }
 
 // one pass of the per-iteration loop body; returns 1 to continue, 0 when the loop ends, -1 on error

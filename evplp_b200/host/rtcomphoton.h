@@ -176,6 +176,33 @@ public:
               "evplp_photon_splat");
     }
     void runLightProgram() { check(evplp_light_pass(mHandle), "evplp_light_pass"); }                    // :839-855
+
+    // Photon counts whose record buffer (96 B x (B+1) per path) would not fit in HBM (BASELINE config 5: up to 2^28 paths =
+    // 103 GB) are streamed: the VPL prefix is traced and gathered first, then the light paths are traced and splatted in
+    // chunks of mMaxPathsPerTrace.  Results are identical to the one-pass order (every path keeps its own RNG stream,
+    // lighttracing.cu:202-203, and the fixed-point splat is order-independent).
+    void setMaxPathsPerTrace(uint64_t n) { mMaxPathsPerTrace = n; }
+    void runStreamed(uint32_t rngSeed) {
+        if (!mDoLightTracing) return;
+        if (mBaseGatherMode == EVPLP_GATHER_LVC && mDoVplSplat)
+            throw std::runtime_error("the LVC gather reads every light path and cannot be streamed; lower numLightPaths");
+        if (mDoVplSplat) {
+            if ((uint64_t)mNumVplLightPaths > mMaxPathsPerTrace) throw std::runtime_error("numVplLightPaths exceeds the streaming chunk");
+            check(evplp_light_trace(mHandle, rngSeed, 0, mNumVplLightPaths), "evplp_light_trace");
+            runOptixVplProgram();
+        }
+        if (!mDoPhotonSplat) return;
+        uint64_t p0 = 0, p1 = mNumLightPaths;
+        if (mPartition == PartitionImage && mWorldSize > 1) {
+            p0 = (uint64_t)mNumLightPaths * (uint64_t)mRank / (uint64_t)mWorldSize;
+            p1 = (uint64_t)mNumLightPaths * (uint64_t)(mRank + 1) / (uint64_t)mWorldSize;
+        }
+        for (uint64_t c = p0; c < p1; c += mMaxPathsPerTrace) {
+            const uint64_t n = std::min<uint64_t>(mMaxPathsPerTrace, p1 - c);
+            check(evplp_light_trace(mHandle, rngSeed, (uint32_t)c, (uint32_t)n), "evplp_light_trace");
+            check(evplp_photon_splat(mHandle, 0, n * mNumPhotonsPerLightPath, nullptr), "evplp_photon_splat");
+        }
+    }
     FloatImage runFinalProgram(float vplScale, float photonScale, float lightScale, bool gamma) {        // :756-787 + dumpImage :225-249
         FloatImage img((size_t)mResolution.x, (size_t)mResolution.y);
         check(evplp_resolve(mHandle, vplScale, photonScale, lightScale, gamma ? 1 : 0, img.data()), "evplp_resolve");
@@ -232,9 +259,13 @@ public:
             pushParams(jitter, (uint32_t)mNumIterations + mRngOffset);
             if (mFrameMode == ClearEveryFrame) check(evplp_clear_accum(mHandle), "evplp_clear_accum");
             if (mDoDeferredShading) runDeferredProgram();
-            if (mDoLightTracing) runOptixLightTracingProgram((uint32_t)mNumIterations + mRngOffset);
-            if (mDoVplSplat) runOptixVplProgram();
-            if (mDoPhotonSplat) runPhotonSplat();
+            if ((uint64_t)mNumLightPaths <= mMaxPathsPerTrace) {
+                if (mDoLightTracing) runOptixLightTracingProgram((uint32_t)mNumIterations + mRngOffset);
+                if (mDoVplSplat) runOptixVplProgram();
+                if (mDoPhotonSplat) runPhotonSplat();
+            } else {
+                runStreamed((uint32_t)mNumIterations + mRngOffset);
+            }
             if (mDoLightRender && (!imageMode || mRank == 0)) runLightProgram();
         }
         mNumIterations++;
@@ -330,6 +361,7 @@ protected:
     }
     int mDevice = 0, mBaseGatherMode = EVPLP_GATHER_VPL, mRank = 0, mWorldSize = 1;
     EPartition mPartition = PartitionIterations;
+    uint64_t mMaxPathsPerTrace = 8ull << 20;  // 8 Mi paths = 3.2 GB of records per chunk
     void* mNcclComm = nullptr;
     bool mWriteOutputs = true;
     evplp_handle mHandle = nullptr;

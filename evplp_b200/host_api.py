@@ -37,6 +37,7 @@ def load_host_library():
     lib.evplp_host_scene_info.argtypes = [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.evplp_host_technique_create.restype = _P
     lib.evplp_host_technique_create.argtypes = [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.evplp_host_technique_set_max_paths_per_trace.argtypes = [_P, C.c_uint64]
     lib.evplp_host_technique_handle.restype = _P
     lib.evplp_host_technique_handle.argtypes = [_P]
     lib.evplp_host_technique_iterate.argtypes = [_P]
@@ -155,6 +156,9 @@ class Technique:
         if not self.h:
             _err(self.lib, "evplp_host_technique_create")
         self._scene = host_scene
+
+    def set_max_paths_per_trace(self, n):
+        self.lib.evplp_host_technique_set_max_paths_per_trace(self.h, n)
 
     def device_handle(self):
         return C.c_void_p(self.lib.evplp_host_technique_handle(self.h))

@@ -192,3 +192,32 @@ def test_bvh_leaf_size_does_not_change_hits():
                 assert np.array_equal(got[0][0], ref[0][0]) and np.array_equal(got[0][1], ref[0][1]) and np.array_equal(got[1][0], ref[1][0])
     finally:
         capi.check(lib, lib.evplp_set_option(None, b"bvh_leaf_max", 2), "opt")
+
+
+def test_streamed_light_paths_equal_one_pass():
+    """BASELINE config 5 machinery: light paths traced + splatted in chunks (record buffer smaller than the photon count)
+    give exactly the one-pass accumulation layers."""
+    W2, H2 = 640, 360
+    hs = HA.HostScene.generate("conference", 1, 3, W2 / H2)
+    fam = {"rngOffset": 1, "numMaxIteration": -1, "timeLimitMs": -1.0, "frameMode": "accumulate", "combinedFilename": "a.pfm",
+           "weightedPhotonFilename": "b.pfm", "weightedVplFilename": "c.pfm", "statFilename": "s.json", "useJitter": True, "useStat": False,
+           "numLightPaths": 100000, "numVplLightPaths": 40, "numMaxBounces": 3, "radiusPercentage": 0.004, "misMode": "geometryClamp",
+           "DoProgressive": True}
+    lib = capi.load_library()
+    out = []
+    for chunk in (None, 30000):
+        t = HA.Technique(hs, fam, W2, H2)
+        if chunk:
+            t.set_max_paths_per_trace(chunk)
+        h = t.device_handle()
+        capi.check(lib, lib.evplp_set_option(h, b"gather_chunks", 1), "opt")
+        for _ in range(2):
+            t.iterate()
+        vpl = np.empty((H2, W2, 3), dtype=np.int64); ph = np.empty((H2, W2, 3), dtype=np.int64); li = np.empty((H2, W2), dtype=np.uint32)
+        capi.check(lib, lib.evplp_download_accum(h, capi.ptr(vpl), capi.ptr(ph), capi.ptr(li)), "download")
+        capi.check(lib, lib.evplp_set_option(h, b"gather_chunks", 0), "opt")
+        t.close()
+        out.append((vpl, ph, li))
+    assert out[0][0].any() and out[0][1].any()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
