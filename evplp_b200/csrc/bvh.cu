@@ -191,24 +191,25 @@ __device__ __forceinline__ float half_area(const float* b) {
 }
 
 // One level of the wide collapse.  Work item = (binary internal node, wide node slot).
+template <int W>
 __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ counters, int level,
                                 uint32_t* __restrict__ queueOut, uint32_t* countersOut,
                                 const int32_t* __restrict__ left, const int32_t* __restrict__ right,
                                 const int32_t* __restrict__ rangeFirst, const int32_t* __restrict__ rangeLast,
                                 const float* __restrict__ nodeBounds, const float* __restrict__ primLo,
                                 const float* __restrict__ primHi, const uint32_t* __restrict__ sorted, float pad, int leafMax,
-                                WideNode* __restrict__ nodes) {
+                                WideNodeT<W>* __restrict__ nodes) {
     // counters: [0] = number of wide nodes allocated, [1 + (level&1)] = items in queueIn, [1 + (~level&1)] = out count
     const uint32_t numIn = counters[1 + (level & 1)];
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= numIn) return;
     const int bin = (int)queueIn[2 * (size_t)w];
     const uint32_t slot = queueIn[2 * (size_t)w + 1];
-    int cand[BVH_WIDTH];
+    int cand[W];
     int nc = 2;
     cand[0] = left[bin];
     cand[1] = right[bin];
-    while (nc < BVH_WIDTH) {
+    while (nc < W) {
         int best = -1;
         float bestArea = -1.f;
         for (int k = 0; k < nc; k++) {
@@ -223,8 +224,8 @@ __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint
         cand[best] = left[c];
         cand[nc++] = right[c];
     }
-    WideNode nd;
-    for (int k = 0; k < BVH_WIDTH; k++) {
+    WideNodeT<W>& nd = nodes[slot];  // written in place (a 32-wide node does not fit in registers)
+    for (int k = 0; k < W; k++) {
         if (k >= nc) {
             // empty slot: a huge FINITE box (no inf * 0 = NaN in the sign-masked slab test) that no ray ever enters
             nd.lox[k] = nd.loy[k] = nd.loz[k] = BVH_EMPTY_COORD;
@@ -252,17 +253,17 @@ __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint
             }
         }
     }
-    nodes[slot] = nd;
 }
 
 // Scene with <= BVH_LEAF_MAX triangles: one node, one leaf child.
+template <int W>
 __global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const float* __restrict__ primHi, float pad,
-                                 WideNode* nodes) {
-    WideNode nd;
+                                 WideNodeT<W>* nodes) {
+    WideNodeT<W>& nd = nodes[0];
     float b[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int i = 0; i < n; i++)
         for (int k = 0; k < 3; k++) { b[k] = fminf(b[k], primLo[3 * i + k]); b[3 + k] = fmaxf(b[3 + k], primHi[3 * i + k]); }
-    for (int k = 0; k < BVH_WIDTH; k++) {
+    for (int k = 0; k < W; k++) {
         nd.lox[k] = nd.loy[k] = nd.loz[k] = BVH_EMPTY_COORD;
         nd.hix[k] = nd.hiy[k] = nd.hiz[k] = BVH_EMPTY_COORD;
         nd.child[k] = BVH_EMPTY;
@@ -270,17 +271,49 @@ __global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const 
     nd.lox[0] = b[0] - pad; nd.loy[0] = b[1] - pad; nd.loz[0] = b[2] - pad;
     nd.hix[0] = b[3] + pad; nd.hiy[0] = b[4] + pad; nd.hiz[0] = b[5] + pad;
     nd.child[0] = bvh_make_leaf(0u, (uint32_t)n);
-    nodes[0] = nd;
 }
 
 extern int g_bvhLeafMax;  // capi.cu: triangles per leaf child (1..8)
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (err) *err = std::string(#x) + ": " + cudaGetErrorString(e_); return e_; } } while (0)
 
+extern int g_shaftLeafMax;  // capi.cu: triangles per leaf child of the 32-wide hierarchy
+
+// Level-by-level collapse of the binary radix tree into W-ary nodes (surface-area guided: the child with
+// the largest box is opened first), leaves of <= leafMax triangles.
+template <int W>
+static cudaError_t run_collapse(EvplpContext* c, WideNodeT<W>* nodes, int leafMax, int* numNodesOut, std::string* err) {
+    cudaStream_t st = c->stream;
+    uint32_t init[4] = {1u, 1u, 0u, 0u};  // one wide node (root), one item in queue A
+    uint32_t rootItem[2] = {0u, 0u};
+    CK(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->queueA.p, rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, st));
+    uint32_t numIn = 1;
+    int level = 0;
+    while (numIn > 0) {
+        uint32_t* qin = (level & 1) ? c->queueB.p : c->queueA.p;
+        uint32_t* qout = (level & 1) ? c->queueA.p : c->queueB.p;
+        CK(cudaMemsetAsync(c->counters.p + 1 + ((level + 1) & 1), 0, sizeof(uint32_t), st));
+        collapse_kernel<W><<<(numIn + 63) / 64, 64, 0, st>>>(qin, c->counters.p, level, qout, c->counters.p, c->left.p, c->right.p,
+                                                             c->rangeFirst.p, c->rangeLast.p, c->nodeBounds.p, c->primLo.p,
+                                                             c->primHi.p, c->primIdsSorted.p, c->boxPad, leafMax, nodes);
+        c->launches++;
+        uint32_t cnt[3];
+        CK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        numIn = cnt[1 + ((level + 1) & 1)];
+        *numNodesOut = (int)cnt[0];
+        level++;
+        if (level > 4096) { if (err) *err = "wide collapse did not terminate"; return cudaErrorUnknown; }
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     const int n = c->numPrims;
     cudaStream_t st = c->stream;
     c->numNodes = 0;
+    c->numShaftNodes = 0;
     c->bvhBuilt = false;
     if (n == 0) { c->bvhBuilt = true; return cudaSuccess; }
     const int nInt = n > 1 ? n - 1 : 0;
@@ -292,6 +325,9 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     CK(c->leafParent.reserve(n)); CK(c->rangeFirst.reserve(nInt)); CK(c->rangeLast.reserve(nInt));
     CK(c->nodeBounds.reserve(6 * (size_t)nInt)); CK(c->refitFlags.reserve(nInt));
     CK(c->nodes.reserve(nInt > 0 ? nInt : 1));
+    // 32-wide nodes: every bottom-level node covers > leafMax triangles of its own and every node with node children is
+    // full (32 children), so there are at most ~n / (leafMax + 1) * 32/31 of them
+    CK(c->shaftNodes.reserve(nInt > 0 ? (size_t)nInt / (size_t)(g_shaftLeafMax + 1) + (size_t)nInt / 16 + 64 : 1));
     CK(c->sceneBoundsEnc.reserve(6));
     CK(c->queueA.reserve(2 * (size_t)(nInt + 1))); CK(c->queueB.reserve(2 * (size_t)(nInt + 1)));
     CK(c->counters.reserve(4));
@@ -329,10 +365,12 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     leaf_records_kernel<<<gridN, TB, 0, st>>>(c->triVerts.p, c->primIdsSorted.p, n, c->triLeaf.p);
     c->launches++;
     if (n <= g_bvhLeafMax) {
-        tiny_root_kernel<<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->nodes.p);
-        c->launches++;
+        tiny_root_kernel<BVH_WIDTH><<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->nodes.p);
+        tiny_root_kernel<SHAFT_WIDTH><<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->shaftNodes.p);
+        c->launches += 2;
         CK(cudaStreamSynchronize(st));
         c->numNodes = 1;
+        c->numShaftNodes = 1;
         c->bvhBuilt = true;
         return cudaSuccess;
     }
@@ -346,29 +384,12 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     refit_kernel<<<gridN, TB, 0, st>>>(n, c->left.p, c->right.p, c->parent.p, c->leafParent.p, c->primLo.p, c->primHi.p,
                                        c->primIdsSorted.p, c->nodeBounds.p, c->refitFlags.p);
     c->launches++;
-    // 7 collapse
-    uint32_t init[4] = {1u, 1u, 0u, 0u};  // one wide node (root), one item in queue A
-    uint32_t rootItem[2] = {0u, 0u};
-    CK(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->queueA.p, rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, st));
-    uint32_t numIn = 1;
-    int level = 0;
-    while (numIn > 0) {
-        uint32_t* qin = (level & 1) ? c->queueB.p : c->queueA.p;
-        uint32_t* qout = (level & 1) ? c->queueA.p : c->queueB.p;
-        CK(cudaMemsetAsync(c->counters.p + 1 + ((level + 1) & 1), 0, sizeof(uint32_t), st));
-        collapse_kernel<<<(numIn + 127) / 128, 128, 0, st>>>(qin, c->counters.p, level, qout, c->counters.p, c->left.p,
-                                                            c->right.p, c->rangeFirst.p, c->rangeLast.p, c->nodeBounds.p,
-                                                            c->primLo.p, c->primHi.p, c->primIdsSorted.p, c->boxPad,
-                                                            g_bvhLeafMax, c->nodes.p);
-        c->launches++;
-        uint32_t cnt[3];
-        CK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        numIn = cnt[1 + ((level + 1) & 1)];
-        c->numNodes = (int)cnt[0];
-        level++;
-        if (level > 4096) { if (err) *err = "wide collapse did not terminate"; return cudaErrorUnknown; }
+    // 7 collapse into the 4-wide per-ray hierarchy and the 32-wide shaft hierarchy
+    {
+        cudaError_t e = run_collapse<BVH_WIDTH>(c, c->nodes.p, g_bvhLeafMax, &c->numNodes, err);
+        if (e != cudaSuccess) return e;
+        e = run_collapse<SHAFT_WIDTH>(c, c->shaftNodes.p, g_shaftLeafMax, &c->numShaftNodes, err);
+        if (e != cudaSuccess) return e;
     }
     CK(cudaGetLastError());
     c->bvhBuilt = true;

@@ -15,6 +15,8 @@ int g_bandStride = 0, g_bandOffset = 0;
 int g_gatherMinBlocks = 3;
 int g_splatGroup = 0;
 int g_bvhLeafMax = BVH_LEAF_MAX;
+int g_shaftLeafMax = 4;
+int g_gatherMode = 0;
 int g_splatMode = 0;
 int g_splatMaxEntries = 256 * 1024 * 1024;
 }
@@ -32,6 +34,7 @@ DevScene EvplpContext::scene() const {
     DevScene s;
     s.triLeaf = triLeaf.p; s.triVerts = triVerts.p; s.triUV = triUV.p; s.mats = mats.p; s.texPool = texPool.p;
     s.lightCdf = lightCdf.p; s.nodes = nodes.p; s.numPrims = numPrims; s.numNodes = numNodes;
+    s.shaftNodes = shaftNodes.p; s.numShaftNodes = numShaftNodes;
     s.lightFirst = lightFirst; s.lightCount = lightCount; s.lightArea = lightArea;
     for (int k = 0; k < 4; k++) { s.lightIntensity[k] = lightIntensity[k]; s.lightDisplay[k] = lightDisplay[k]; }
     return s;
@@ -113,7 +116,7 @@ int evplp_destroy(evplp_handle c) {
     c->lightCdf.release(); c->primLo.release(); c->primHi.release(); c->codes.release(); c->codesSorted.release();
     c->primIds.release(); c->primIdsSorted.release(); c->left.release(); c->right.release(); c->parent.release();
     c->leafParent.release(); c->rangeFirst.release(); c->rangeLast.release(); c->nodeBounds.release();
-    c->refitFlags.release(); c->nodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
+    c->refitFlags.release(); c->nodes.release(); c->shaftNodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
     c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->records.release();
     c->vplList.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
     c->accPhoton.release(); c->accLight.release(); c->resolveOut.release(); c->devStats.release();
@@ -598,6 +601,8 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
     if (strcmp(name, "gather_band_offset") == 0) { NEED(value >= 0, "gather_band_offset must be >= 0"); evplp::g_bandOffset = value; return EVPLP_OK; }
     if (strcmp(name, "gather_min_blocks") == 0) { evplp::g_gatherMinBlocks = value; return EVPLP_OK; }
     if (strcmp(name, "bvh_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "bvh_leaf_max must be 1..8"); evplp::g_bvhLeafMax = value; return EVPLP_OK; }
+    if (strcmp(name, "shaft_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "shaft_leaf_max must be 1..8"); evplp::g_shaftLeafMax = value; return EVPLP_OK; }
+    if (strcmp(name, "gather_mode") == 0) { evplp::g_gatherMode = value; return EVPLP_OK; }
     if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }
     if (strcmp(name, "splat_mode") == 0) { evplp::g_splatMode = value; return EVPLP_OK; }
     if (strcmp(name, "splat_max_entries") == 0) { evplp::g_splatMaxEntries = value; return EVPLP_OK; }

@@ -66,6 +66,8 @@ struct EvplpContext {
     evplp::DevBuf<float> nodeBounds;              // 6 floats per binary internal node
     evplp::DevBuf<uint32_t> refitFlags;
     evplp::DevBuf<evplp::WideNode> nodes;
+    evplp::DevBuf<evplp::ShaftNode> shaftNodes;
+    int numShaftNodes = 0;
     evplp::DevBuf<uint32_t> sceneBoundsEnc;       // 6 ordered-uint encodings
     evplp::DevBuf<uint8_t> sortTemp;
     evplp::DevBuf<uint32_t> queueA, queueB, counters;

@@ -28,11 +28,15 @@ constexpr uint32_t BVH_LEAF_BIT = 0x80000000u;
 constexpr int BVH_STACK = 96;
 constexpr float BVH_EMPTY_COORD = 3.0e38f;   // box of an empty child slot (finite, beyond any scene)
 
-struct alignas(128) WideNode {
-    float lox[BVH_WIDTH], loy[BVH_WIDTH], loz[BVH_WIDTH];
-    float hix[BVH_WIDTH], hiy[BVH_WIDTH], hiz[BVH_WIDTH];
-    uint32_t child[BVH_WIDTH];  // EMPTY | LEAF_BIT | (count-1) << 27 | first   or   node index
+template <int W>
+struct alignas(128) WideNodeT {
+    float lox[W], loy[W], loz[W];
+    float hix[W], hiy[W], hiz[W];
+    uint32_t child[W];  // EMPTY | LEAF_BIT | (count-1) << 27 | first   or   node index
 };
+using WideNode = WideNodeT<BVH_WIDTH>;   // 128 B: per-ray traversals (closest hit, per-lane / packet any hit)
+constexpr int SHAFT_WIDTH = 32;          // one child per lane: warp-cooperative shaft traversal of the gather
+using ShaftNode = WideNodeT<SHAFT_WIDTH>;  // 896 B, every plane array is one coalesced 128-byte row
 
 EVPLP_HD uint32_t bvh_make_leaf(uint32_t first, uint32_t count) { return BVH_LEAF_BIT | ((count - 1u) << 27) | first; }
 EVPLP_HD uint32_t bvh_leaf_first(uint32_t c) { return c & 0x07ffffffu; }
@@ -46,6 +50,8 @@ struct DevScene {
     const float4* texPool;
     const float* lightCdf;
     const WideNode* nodes;
+    const ShaftNode* shaftNodes;  // 32-wide hierarchy over the same triangles (same leaf order)
+    int numShaftNodes;
     int numPrims;
     int numNodes;
     int lightFirst, lightCount;
@@ -351,6 +357,108 @@ __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V
         }
     }
     return active && !open;
+}
+
+// ---- shaft traversal of the 32-wide hierarchy ---------------------------------------------------
+// All 32 shadow rays of a warp start at the same point (the VPL) and end inside the warp's pixel
+// tile, so they lie in the shaft  S(t) = vpl + t * ([tileLo, tileHi] - vpl),  t in [tmin, tmax]
+// (same parameter t as the rays).  Instead of 32 lanes x 4 child boxes of per-ray slab tests, ONE
+// conservative shaft-vs-box test per child decides where the warp descends, and the 32 lanes test 32
+// children of a 32-wide node at once (one coalesced 128-byte row per plane array).  The descent only
+// COLLECTS candidate leaves; every lane then runs the exact triangle test of its own ray against the
+// candidates' triangles, so the result per ray is the same "exists a triangle that the branchless test
+// accepts" as everywhere else -- the shaft is just another conservative cull.
+constexpr int SHAFT_CAND = 24;  // candidate leaves per (warp, VPL); more => fall back to the per-ray packet traversal
+
+struct Shaft {
+    float ilx, ily, ilz, ihx, ihy, ihz;  // 1 / (tileLo - vpl), 1 / (tileHi - vpl) per axis
+    V3 apex;
+    unsigned signs;                      // bit a: tileLo_a - vpl_a > 0, bit 3 + a: tileHi_a - vpl_a > 0
+};
+
+__device__ __forceinline__ Shaft make_shaft(V3 apex, V3 tileLo, V3 tileHi) {
+    Shaft s;
+    s.apex = apex;
+    float dl[3] = {tileLo.x - apex.x, tileLo.y - apex.y, tileLo.z - apex.z};
+    float dh[3] = {tileHi.x - apex.x, tileHi.y - apex.y, tileHi.z - apex.z};
+    unsigned sg = 0;
+    float il[3], ih[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        // a zero extent keeps its constraint ("t * 0 <= A" / "t * 0 >= B") as a huge bound of the right sign
+        if (fabsf(dl[a]) < 1e-30f) dl[a] = -1e-30f;
+        if (fabsf(dh[a]) < 1e-30f) dh[a] = 1e-30f;
+        if (dl[a] > 0.f) sg |= 1u << a;
+        if (dh[a] > 0.f) sg |= 8u << a;
+        il[a] = rcp_approx(dl[a]);
+        ih[a] = rcp_approx(dh[a]);
+    }
+    s.ilx = il[0]; s.ily = il[1]; s.ilz = il[2]; s.ihx = ih[0]; s.ihy = ih[1]; s.ihz = ih[2];
+    s.signs = sg;
+    return s;
+}
+
+// exists t in [tmin, tmax] with  apex + t * dlo <= bhi  and  apex + t * dhi >= blo  on every axis
+__device__ __forceinline__ bool shaft_overlap(const Shaft& s, float blx, float bly, float blz, float bhx, float bhy, float bhz,
+                                              float tmin, float tmax) {
+    const float ax = (bhx - s.apex.x) * s.ilx, bx = (blx - s.apex.x) * s.ihx;
+    const float ay = (bhy - s.apex.y) * s.ily, by = (bly - s.apex.y) * s.ihy;
+    const float az = (bhz - s.apex.z) * s.ilz, bz = (blz - s.apex.z) * s.ihz;
+    const float NI = -INFINITY, PI = INFINITY;
+    // dlo > 0: a is an upper bound, else a lower bound;  dhi > 0: b is a lower bound, else an upper bound
+    float lo = fmaxf(fmaxf((s.signs & 1u) ? NI : ax, (s.signs & 8u) ? bx : NI), fmaxf((s.signs & 2u) ? NI : ay, (s.signs & 16u) ? by : NI));
+    lo = fmaxf(lo, fmaxf(fmaxf((s.signs & 4u) ? NI : az, (s.signs & 32u) ? bz : NI), tmin));
+    float hi = fminf(fminf((s.signs & 1u) ? ax : PI, (s.signs & 8u) ? PI : bx), fminf((s.signs & 2u) ? ay : PI, (s.signs & 16u) ? PI : by));
+    hi = fminf(hi, fminf(fminf((s.signs & 4u) ? az : PI, (s.signs & 32u) ? PI : bz), tmax));
+    return lo <= hi;
+}
+
+// Returns per lane whether its ray (org = shaft apex, dir) is occluded.  Must be called by all 32 lanes.
+__device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 org, V3 dir, float tmin, float tmax, const Shaft& sh,
+                                            uint32_t* warpStack /* BVH_STACK entries */, uint32_t* cand /* SHAFT_CAND entries */,
+                                            int* overflow) {
+    const unsigned full = 0xffffffffu;
+    if (sc.numShaftNodes == 0 || !__any_sync(full, active)) return false;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int sp = 0, cn = 0;
+    uint32_t cur = 0;
+    bool fallback = false;
+    while (true) {
+        const ShaftNode* nd = sc.shaftNodes + cur;
+        const uint32_t word = __ldg(&nd->child[lane]);
+        const bool hit = word != BVH_EMPTY &&
+                         shaft_overlap(sh, __ldg(&nd->lox[lane]), __ldg(&nd->loy[lane]), __ldg(&nd->loz[lane]), __ldg(&nd->hix[lane]),
+                                       __ldg(&nd->hiy[lane]), __ldg(&nd->hiz[lane]), tmin, tmax);
+        const bool leaf = (word & BVH_LEAF_BIT) != 0u;
+        const unsigned mi = __ballot_sync(full, hit && !leaf), ml = __ballot_sync(full, hit && leaf);
+        const int ni = __popc(mi), nl = __popc(ml);
+        if (sp + ni > BVH_STACK || cn + nl > SHAFT_CAND) { fallback = true; break; }
+        if (hit && !leaf) warpStack[sp + __popc(mi & lt)] = word;
+        if (hit && leaf) cand[cn + __popc(ml & lt)] = word;
+        sp += ni; cn += nl;
+        __syncwarp();
+        if (sp == 0) break;
+        cur = warpStack[--sp];
+    }
+    if (fallback) {  // fat shaft (tile across a depth edge) or cluttered region: per-ray packet traversal
+        __syncwarp();
+        return trace_any_warp(sc, active, org, dir, tmin, tmax, warpStack, overflow);
+    }
+    bool occ = false;
+    for (int k = 0; k < cn; k++) {
+        const uint32_t w = cand[k];
+        const uint32_t first = bvh_leaf_first(w), count = bvh_leaf_count(w);
+        const float4* tp = sc.triLeaf + 4 * (size_t)first;
+        for (uint32_t j = 0; j < count; j++, tp += 4) {
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+            float t, be, ga;
+            occ |= tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga);
+        }
+        if (!__any_sync(full, active && !occ)) break;
+    }
+    __syncwarp();
+    return active && occ;
 }
 
 #endif  // __CUDACC__

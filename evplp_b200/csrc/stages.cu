@@ -234,7 +234,7 @@ struct GatherParams {
     int bandStride, bandOffset;  // this launch owns the 16-row bands b = bandOffset (mod bandStride) of the tile (multi-GPU interleave)
 };
 
-template <int MINB>
+template <int MINB, bool SHAFT>
 __global__ void __launch_bounds__(GATHER_WARPS * 32, MINB)
 gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf, const EvplpRecord* __restrict__ records,
                   const uint32_t* __restrict__ vplList, const uint32_t* __restrict__ vplCount, long long* __restrict__ acc,
@@ -243,6 +243,7 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     // culled by the cosine test run ahead instead of waiting for the slowest warp of the block).
     __shared__ float4 batchAll[GATHER_WARPS][GATHER_BATCH * 6];
     __shared__ uint32_t stacks[GATHER_WARPS][BVH_STACK];
+    __shared__ uint32_t cands[SHAFT ? GATHER_WARPS : 1][SHAFT_CAND];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* batch = batchAll[warp];
     const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -254,6 +255,14 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     Surface sf = load_surface(gbuf, n, i, &gw);
     const bool valid = inside && gw != 0.0f;
     const V3 wi01 = normalize(gp.cameraPosition - sf.pos);
+    // bounds of the warp's surface points: the far end of every (VPL -> tile) shaft
+    V3 tileLo = valid ? sf.pos : v3s(INFINITY), tileHi = valid ? sf.pos : v3s(-INFINITY);
+    if (SHAFT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            tileLo = vmin(tileLo, v3(__shfl_xor_sync(0xffffffffu, tileLo.x, o), __shfl_xor_sync(0xffffffffu, tileLo.y, o), __shfl_xor_sync(0xffffffffu, tileLo.z, o)));
+            tileHi = vmax(tileHi, v3(__shfl_xor_sync(0xffffffffu, tileHi.x, o), __shfl_xor_sync(0xffffffffu, tileHi.y, o), __shfl_xor_sync(0xffffffffu, tileHi.z, o)));
+        }
+    }
 
     const uint32_t total = *vplCount;
     const uint32_t per = (total + gp.numChunks - 1) / gp.numChunks;
@@ -281,7 +290,13 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
             const bool active = valid && !(c1c2 <= 0.000f);
             rays += active ? 1u : 0u;
             // Ray(vpl.pos, -v12, shadow, 0.0001, 1 - 0.0001) -- lighttracing.cu:292
-            const bool occluded = trace_any_warp(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
+            bool occluded;
+            if (SHAFT) {
+                const Shaft sh = make_shaft(vpos, tileLo, tileHi);
+                occluded = trace_any_warp_shaft(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stacks[warp], cands[warp], &ovf);
+            } else {
+                occluded = trace_any_warp(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
+            }
             if (active && !occluded) {
                 const Vertex vp = load_vertex(&batch[j * 6]);
                 result += vpl_shade(sf, wi01, vp, v12, c1c2, gp.misMode, gp.pdfMc, gp.clampingValue);
@@ -850,6 +865,7 @@ extern int g_bandStride, g_bandOffset;  // capi.cu: 16-row band interleave of th
 extern int g_splatGroup;       // capi.cu: lanes per photon in the scatter splat (0 = 32; 1 / 8 / 32)
 extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatter splat
 extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
+extern int g_gatherMode;       // capi.cu: 0 = per-ray packet traversal, 1 = shaft traversal of the 32-wide hierarchy
 extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
 
 static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
@@ -926,10 +942,14 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         c->launches++;
     }
     c->stageBegin(ST_GATHER);
-    switch (g_gatherMinBlocks) {
-        case 2: gather_vpl_kernel<2><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
-        case 4: gather_vpl_kernel<4><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
-        default: gather_vpl_kernel<3><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+    if (g_gatherMode == 1) {
+        gather_vpl_kernel<3, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+    } else {
+        switch (g_gatherMinBlocks) {
+            case 2: gather_vpl_kernel<2, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+            case 4: gather_vpl_kernel<4, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+            default: gather_vpl_kernel<3, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+        }
     }
     c->stageEnd(ST_GATHER);
     c->launches++;

@@ -151,8 +151,11 @@ def _setup_iteration(rig, P, seed=3):
     return planes, prims, rec
 
 
+@pytest.mark.parametrize("gather_mode", [0, 1])
 @pytest.mark.parametrize("mis", [0, 1, 2, 3, 4, 5])
-def test_vpl_gather_all_mis_modes(rig, mis):
+def test_vpl_gather_all_mis_modes(rig, mis, gather_mode):
+    """gather_mode 0 = per-ray packet traversal, 1 = shaft traversal of the 32-wide hierarchy: both bit-exact."""
+    rig.dev.set_option("gather_mode", gather_mode)
     P = rig.params(mis_mode=mis, accumulate=False)
     planes, prims, rec = _setup_iteration(rig, P)
     exp, cnt = rig.orc.vpl_gather(P, W, H, planes, prims, rec, capi.GATHER_VPL)
@@ -172,6 +175,7 @@ def test_vpl_gather_all_mis_modes(rig, mis):
     rig.dev.vpl_gather(capi.GATHER_VPL)
     vpl5, _, _ = rig.dev.download_accum()
     rig.dev.set_option("gather_chunks", 0)
+    rig.dev.set_option("gather_mode", 0)
     a, b = vpl5.astype(np.float64), eacc.astype(np.float64)
     assert (np.abs(a - b) <= 6 + 1e-5 * np.abs(b)).all()  # 1e-5 relative + a few Q31.32 quanta (one rounding per chunk)
 
