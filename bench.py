@@ -330,6 +330,11 @@ def run_gpu(args):
             "e2e": {"value": e2e_pairs / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 3200 + C.sizeof(capi.Params),
                     "d2h_bytes_per_step": RES_X * RES_Y * 12 + 16},
         }
+        dbg = (C.c_uint64 * 8)()
+        ck(lib.evplp_debug_counters(h, dbg), "debug_counters")
+        if dbg[0]:
+            line["shaft_gather"] = {"steps": int(dbg[0]), "fallback_frac": dbg[1] / dbg[0], "nodes_per_step": dbg[2] / dbg[0],
+                                    "candidate_leaves_per_step": dbg[3] / max(dbg[0] - dbg[1], 1), "nodes4": int(dbg[4]), "nodes32": int(dbg[5])}
         if world == 1 and not args.no_cpu:
             pps, csec, cores, desc = cpu_sample(1, 0)
             line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc}

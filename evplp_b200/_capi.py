@@ -121,6 +121,7 @@ SYMBOLS = {
     "evplp_last_stage_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "evplp_synchronize": (C.c_int, [_P]),
     "evplp_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "evplp_debug_counters": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "evplp_event_record": (C.c_int, [_P, C.c_int]),
     "evplp_event_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "evplp_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

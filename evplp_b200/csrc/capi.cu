@@ -15,8 +15,9 @@ int g_bandStride = 0, g_bandOffset = 0;
 int g_gatherMinBlocks = 3;
 int g_splatGroup = 0;
 int g_bvhLeafMax = BVH_LEAF_MAX;
-int g_shaftLeafMax = 4;
-int g_gatherMode = 0;
+int g_shaftLeafMax = 2;
+int g_gatherMode = 1;   // 1 = shaft traversal of the 32-wide hierarchy (default), 0 = per-ray packet traversal
+int g_shaftCandMax = 24;
 int g_splatMode = 0;
 int g_splatMaxEntries = 256 * 1024 * 1024;
 }
@@ -578,6 +579,17 @@ int evplp_launch_count(evplp_handle c, uint64_t* count) {
     return EVPLP_OK;
 }
 
+int evplp_debug_counters(evplp_handle c, uint64_t out[8]) {
+    NEED(c != nullptr && out != nullptr, "evplp_debug_counters: NULL argument");
+    CU(cudaSetDevice(c->device));
+    DevStats ds;
+    CU(cudaMemcpyAsync(&ds, c->devStats.p, sizeof(ds), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out[0] = ds.shaftSteps; out[1] = ds.shaftFallbacks; out[2] = ds.shaftNodeVisits; out[3] = ds.shaftCandLeaves;
+    out[4] = (uint64_t)c->numNodes; out[5] = (uint64_t)c->numShaftNodes; out[6] = 0; out[7] = 0;
+    return EVPLP_OK;
+}
+
 int evplp_event_record(evplp_handle c, int slot) {
     NEED(c != nullptr && slot >= 0 && slot < 4, "evplp_event_record: bad argument");
     CU(cudaSetDevice(c->device));
@@ -602,6 +614,7 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
     if (strcmp(name, "gather_min_blocks") == 0) { evplp::g_gatherMinBlocks = value; return EVPLP_OK; }
     if (strcmp(name, "bvh_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "bvh_leaf_max must be 1..8"); evplp::g_bvhLeafMax = value; return EVPLP_OK; }
     if (strcmp(name, "shaft_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "shaft_leaf_max must be 1..8"); evplp::g_shaftLeafMax = value; return EVPLP_OK; }
+    if (strcmp(name, "shaft_max_candidates") == 0) { evplp::g_shaftCandMax = value; return EVPLP_OK; }
     if (strcmp(name, "gather_mode") == 0) { evplp::g_gatherMode = value; return EVPLP_OK; }
     if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }
     if (strcmp(name, "splat_mode") == 0) { evplp::g_splatMode = value; return EVPLP_OK; }

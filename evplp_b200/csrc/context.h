@@ -30,6 +30,7 @@ enum Stage { ST_BVH = 0, ST_GBUFFER, ST_LIGHT_TRACE, ST_GATHER, ST_SPLAT, ST_RES
 
 struct DevStats {
     unsigned long long shadowRays, splatPhotons, splatFragments, closestRays, gatherPairs;
+    unsigned long long shaftSteps, shaftFallbacks, shaftNodeVisits, shaftCandLeaves;  // tuning counters of the shaft gather
     int stackOverflow;
     int pad;
 };

@@ -368,12 +368,16 @@ __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V
 // COLLECTS candidate leaves; every lane then runs the exact triangle test of its own ray against the
 // candidates' triangles, so the result per ray is the same "exists a triangle that the branchless test
 // accepts" as everywhere else -- the shaft is just another conservative cull.
-constexpr int SHAFT_CAND = 24;  // candidate leaves per (warp, VPL); more => fall back to the per-ray packet traversal
+constexpr int SHAFT_CAND = 32;  // capacity of the candidate-leaf list; the launch-time limit (shaft_max_candidates) is <= this
 
 struct Shaft {
     float ilx, ily, ilz, ihx, ihy, ihz;  // 1 / (tileLo - vpl), 1 / (tileHi - vpl) per axis
     V3 apex;
     unsigned signs;                      // bit a: tileLo_a - vpl_a > 0, bit 3 + a: tileHi_a - vpl_a > 0
+    // fast path (no axis on which the tile straddles the apex): entry / exit plane of every axis selected by ADDRESS
+    int sorted;                          // 1 = fast path usable
+    int nOffX, nOffY, nOffZ, fOffX, fOffY, fOffZ;  // float offsets of the entry / exit plane rows inside a ShaftNode
+    float nix, niy, niz, fix, fiy, fiz;  // matching reciprocals
 };
 
 __device__ __forceinline__ Shaft make_shaft(V3 apex, V3 tileLo, V3 tileHi) {
@@ -383,18 +387,30 @@ __device__ __forceinline__ Shaft make_shaft(V3 apex, V3 tileLo, V3 tileHi) {
     float dh[3] = {tileHi.x - apex.x, tileHi.y - apex.y, tileHi.z - apex.z};
     unsigned sg = 0;
     float il[3], ih[3];
+    int nOff[3], fOff[3];
+    float ni[3], fi[3];
+    int sorted = 1;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         // a zero extent keeps its constraint ("t * 0 <= A" / "t * 0 >= B") as a huge bound of the right sign
         if (fabsf(dl[a]) < 1e-30f) dl[a] = -1e-30f;
         if (fabsf(dh[a]) < 1e-30f) dh[a] = 1e-30f;
-        if (dl[a] > 0.f) sg |= 1u << a;
-        if (dh[a] > 0.f) sg |= 8u << a;
+        const bool lp = dl[a] > 0.f, hp = dh[a] > 0.f;
+        if (lp) sg |= 1u << a;
+        if (hp) sg |= 8u << a;
         il[a] = rcp_approx(dl[a]);
         ih[a] = rcp_approx(dh[a]);
+        // whole tile on the + side of the apex: t >= (blo - apex) / dhi and t <= (bhi - apex) / dlo;
+        // whole tile on the - side:            t >= (bhi - apex) / dlo and t <= (blo - apex) / dhi
+        if (lp != hp) sorted = 0;
+        nOff[a] = (lp ? a : 3 + a) * SHAFT_WIDTH; fOff[a] = (lp ? 3 + a : a) * SHAFT_WIDTH;
+        ni[a] = lp ? ih[a] : il[a]; fi[a] = lp ? il[a] : ih[a];
     }
     s.ilx = il[0]; s.ily = il[1]; s.ilz = il[2]; s.ihx = ih[0]; s.ihy = ih[1]; s.ihz = ih[2];
     s.signs = sg;
+    s.sorted = sorted;
+    s.nOffX = nOff[0]; s.nOffY = nOff[1]; s.nOffZ = nOff[2]; s.fOffX = fOff[0]; s.fOffY = fOff[1]; s.fOffZ = fOff[2];
+    s.nix = ni[0]; s.niy = ni[1]; s.niz = ni[2]; s.fix = fi[0]; s.fiy = fi[1]; s.fiz = fi[2];
     return s;
 }
 
@@ -416,7 +432,8 @@ __device__ __forceinline__ bool shaft_overlap(const Shaft& s, float blx, float b
 // Returns per lane whether its ray (org = shaft apex, dir) is occluded.  Must be called by all 32 lanes.
 __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 org, V3 dir, float tmin, float tmax, const Shaft& sh,
                                             uint32_t* warpStack /* BVH_STACK entries */, uint32_t* cand /* SHAFT_CAND entries */,
-                                            int* overflow) {
+                                            int candMax /* more candidate leaves than this => per-ray packet traversal */, int* overflow,
+                                            unsigned* counters /* [0] fallbacks [1] node visits [2] candidate leaves (per warp) */) {
     const unsigned full = 0xffffffffu;
     if (sc.numShaftNodes == 0 || !__any_sync(full, active)) return false;
     const int lane = threadIdx.x & 31;
@@ -426,14 +443,24 @@ __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 
     bool fallback = false;
     while (true) {
         const ShaftNode* nd = sc.shaftNodes + cur;
+        counters[1]++;
         const uint32_t word = __ldg(&nd->child[lane]);
-        const bool hit = word != BVH_EMPTY &&
-                         shaft_overlap(sh, __ldg(&nd->lox[lane]), __ldg(&nd->loy[lane]), __ldg(&nd->loz[lane]), __ldg(&nd->hix[lane]),
-                                       __ldg(&nd->hiy[lane]), __ldg(&nd->hiz[lane]), tmin, tmax);
+        bool hit;
+        if (sh.sorted) {
+            const float* row = reinterpret_cast<const float*>(nd) + lane;
+            const float tnx = (__ldg(row + sh.nOffX) - sh.apex.x) * sh.nix, tfx = (__ldg(row + sh.fOffX) - sh.apex.x) * sh.fix;
+            const float tny = (__ldg(row + sh.nOffY) - sh.apex.y) * sh.niy, tfy = (__ldg(row + sh.fOffY) - sh.apex.y) * sh.fiy;
+            const float tnz = (__ldg(row + sh.nOffZ) - sh.apex.z) * sh.niz, tfz = (__ldg(row + sh.fOffZ) - sh.apex.z) * sh.fiz;
+            hit = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin)) <= fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+        } else {
+            hit = shaft_overlap(sh, __ldg(&nd->lox[lane]), __ldg(&nd->loy[lane]), __ldg(&nd->loz[lane]), __ldg(&nd->hix[lane]),
+                                __ldg(&nd->hiy[lane]), __ldg(&nd->hiz[lane]), tmin, tmax);
+        }
+        hit = hit && word != BVH_EMPTY;
         const bool leaf = (word & BVH_LEAF_BIT) != 0u;
         const unsigned mi = __ballot_sync(full, hit && !leaf), ml = __ballot_sync(full, hit && leaf);
         const int ni = __popc(mi), nl = __popc(ml);
-        if (sp + ni > BVH_STACK || cn + nl > SHAFT_CAND) { fallback = true; break; }
+        if (sp + ni > BVH_STACK || cn + nl > candMax) { fallback = true; break; }
         if (hit && !leaf) warpStack[sp + __popc(mi & lt)] = word;
         if (hit && leaf) cand[cn + __popc(ml & lt)] = word;
         sp += ni; cn += nl;
@@ -442,9 +469,11 @@ __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 
         cur = warpStack[--sp];
     }
     if (fallback) {  // fat shaft (tile across a depth edge) or cluttered region: per-ray packet traversal
+        counters[0]++;
         __syncwarp();
         return trace_any_warp(sc, active, org, dir, tmin, tmax, warpStack, overflow);
     }
+    counters[2] += (unsigned)cn;
     bool occ = false;
     for (int k = 0; k < cn; k++) {
         const uint32_t w = cand[k];

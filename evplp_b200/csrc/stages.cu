@@ -231,6 +231,7 @@ struct GatherParams {
     unsigned numChunks;  // VPL list split over gridDim.z
     float vslRadius, vslInvPiRadius2;
     unsigned numLightPaths, numVplLightPaths, B1;
+    int shaftCandMax;            // shaft gather: candidate leaves beyond which a (warp, VPL) step falls back to the packet traversal
     int bandStride, bandOffset;  // this launch owns the 16-row bands b = bandOffset (mod bandStride) of the tile (multi-GPU interleave)
 };
 
@@ -271,6 +272,7 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
 
     V3 result = v3s(0.0f);
     unsigned rays = 0;
+    unsigned shaftCnt[3] = {0u, 0u, 0u}, shaftSteps = 0u;
     int ovf = 0;
     for (uint32_t base = begin; base < end; base += GATHER_BATCH) {
         const uint32_t nb = min((uint32_t)GATHER_BATCH, end - base);
@@ -293,7 +295,8 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
             bool occluded;
             if (SHAFT) {
                 const Shaft sh = make_shaft(vpos, tileLo, tileHi);
-                occluded = trace_any_warp_shaft(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stacks[warp], cands[warp], &ovf);
+                occluded = trace_any_warp_shaft(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stacks[warp], cands[warp], gp.shaftCandMax, &ovf, shaftCnt);
+                shaftSteps += __any_sync(0xffffffffu, active) ? 1u : 0u;
             } else {
                 occluded = trace_any_warp(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
             }
@@ -306,6 +309,10 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     if (ovf) stats->stackOverflow = 1;
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
     if (lane == 0 && rays) atomicAdd(&stats->shadowRays, (unsigned long long)rays);
+    if (SHAFT && lane == 0 && shaftSteps) {
+        atomicAdd(&stats->shaftSteps, (unsigned long long)shaftSteps); atomicAdd(&stats->shaftFallbacks, (unsigned long long)shaftCnt[0]);
+        atomicAdd(&stats->shaftNodeVisits, (unsigned long long)shaftCnt[1]); atomicAdd(&stats->shaftCandLeaves, (unsigned long long)shaftCnt[2]);
+    }
     if (!inside) return;
     const V3 out = result * gp.invNumVpl;  // result / (float)numVplLightPaths (reciprocal multiply, lighttracing.cu:378)
     const long long q[3] = {to_fixed(out.x), to_fixed(out.y), to_fixed(out.z)};
@@ -865,6 +872,7 @@ extern int g_bandStride, g_bandOffset;  // capi.cu: 16-row band interleave of th
 extern int g_splatGroup;       // capi.cu: lanes per photon in the scatter splat (0 = 32; 1 / 8 / 32)
 extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatter splat
 extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
+extern int g_shaftCandMax;     // capi.cu
 extern int g_gatherMode;       // capi.cu: 0 = per-ray packet traversal, 1 = shaft traversal of the 32-wide hierarchy
 extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
 
@@ -879,6 +887,7 @@ static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
     g.numChunks = 1;
     g.vslRadius = P.vslRadius; g.vslInvPiRadius2 = P.vslInvPiRadius2;
     g.numLightPaths = P.numLightPaths; g.numVplLightPaths = P.numVplLightPaths; g.B1 = P.numPhotonsPerLightPath;
+    g.shaftCandMax = g_shaftCandMax < 1 ? 1 : (g_shaftCandMax > SHAFT_CAND ? SHAFT_CAND : g_shaftCandMax);
     g.bandStride = g_bandStride > 0 ? g_bandStride : 1;
     g.bandOffset = g_bandStride > 0 ? g_bandOffset : 0;
     return g;

@@ -239,6 +239,9 @@ int evplp_last_stage_ms(evplp_handle h, int stage, float* ms);
 int evplp_synchronize(evplp_handle h);
 /* Number of kernel launches issued by this handle since creation (bench.py gpu_launches). */
 int evplp_launch_count(evplp_handle h, uint64_t* count);
+/* Tuning counters since the last evplp_reset_stats: [0] (warp, VPL) steps of the shaft gather, [1] steps that fell back to the
+ * per-ray packet traversal, [2] 32-wide nodes visited, [3] candidate leaves tested, [4] 4-wide nodes, [5] 32-wide nodes. */
+int evplp_debug_counters(evplp_handle h, uint64_t out[8]);
 /* CUDA events on the handle's stream (4 slots): device-side timing of any span of calls. */
 int evplp_event_record(evplp_handle h, int slot);
 int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
@@ -247,8 +250,11 @@ int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
  * order in one thread, which makes the gather bit-identical to the scalar oracle).
  * "gather_band_stride" / "gather_band_offset": the gather only renders the 16-row bands b = offset (mod stride) of its
  * tile -- the interleaved image partition of a single heavy frame over N GPUs (stride = N, offset = rank).
- * "bvh_leaf_max" (before evplp_build_bvh), "gather_min_blocks", "splat_mode" (0 tiled, 1 scatter), "splat_group",
- * "splat_max_entries": kernel variants.  Options are process-wide; the handle may be NULL. */
+ * "gather_mode": 1 (default) = the warp descends a 32-wide hierarchy with one conservative shaft-vs-box test per child
+ * and runs the exact per-ray triangle tests on the collected candidate leaves; 0 = per-ray packet traversal of the 4-wide
+ * hierarchy.  "shaft_max_candidates" (candidate leaves per step before falling back to mode 0, <= 32),
+ * "bvh_leaf_max" / "shaft_leaf_max" (before evplp_build_bvh), "gather_min_blocks", "splat_mode" (0 tiled, 1 scatter),
+ * "splat_group", "splat_max_entries": kernel variants.  Options are process-wide; the handle may be NULL. */
 int evplp_set_option(evplp_handle h, const char* name, int value);
 
 #ifdef __cplusplus

@@ -4,5 +4,5 @@
 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q -x 2>&1 | tail -2
 for o in "$@"; do
   flags=""; IFS=',' read -ra parts <<< "$o"; for p in "${parts[@]}"; do flags="$flags --opt $p"; done
-  python bench.py --steps 2 --warmup 1 --no-cpu --vpl-paths 512 $flags 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$o pairs/s %.4g rays/s %.4g' % (d['value'], d['shadow_rays_per_s']), d['stage_ms_per_step_rank0'])"
+  python bench.py --steps 2 --warmup 1 --no-cpu --vpl-paths 512 $flags 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$o pairs/s %.4g rays/s %.4g' % (d['value'], d['shadow_rays_per_s']), d['stage_ms_per_step_rank0'], d.get('shaft_gather'))"
 done

@@ -74,11 +74,11 @@ def test_gather_crop_matches_oracle_bit_for_bit(conf):
     exp, _ = orc.vpl_gather(P, W, H, planes, prims, rec, capi.GATHER_VPL, tile=(x0, y0, x0 + tw, y0 + th))
     eacc = np.zeros((H, W, 3), dtype=np.int64)
     orc.accumulate_fixed(exp, eacc)
-    # the shaft traversal gives the same image bit for bit
-    dev.set_option("gather_chunks", 1); dev.set_option("gather_mode", 1)
+    # the per-ray packet traversal (gather_mode 0) gives the same image bit for bit as the default shaft traversal
+    dev.set_option("gather_chunks", 1); dev.set_option("gather_mode", 0)
     dev.clear_accum(); dev.vpl_gather(capi.GATHER_VPL)
     shaft, _, _ = dev.download_accum()
-    dev.set_option("gather_chunks", 0); dev.set_option("gather_mode", 0)
+    dev.set_option("gather_chunks", 0); dev.set_option("gather_mode", 1)
     assert np.array_equal(shaft[y0:y0 + th, x0:x0 + tw], eacc[y0:y0 + th, x0:x0 + tw])
     whole = conf.get("whole_vpl")
     if whole is not None:

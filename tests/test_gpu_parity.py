@@ -175,7 +175,7 @@ def test_vpl_gather_all_mis_modes(rig, mis, gather_mode):
     rig.dev.vpl_gather(capi.GATHER_VPL)
     vpl5, _, _ = rig.dev.download_accum()
     rig.dev.set_option("gather_chunks", 0)
-    rig.dev.set_option("gather_mode", 0)
+    rig.dev.set_option("gather_mode", 1)  # back to the default
     a, b = vpl5.astype(np.float64), eacc.astype(np.float64)
     assert (np.abs(a - b) <= 6 + 1e-5 * np.abs(b)).all()  # 1e-5 relative + a few Q31.32 quanta (one rounding per chunk)
 
