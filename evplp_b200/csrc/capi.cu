@@ -12,7 +12,7 @@ using namespace evplp;
 namespace evplp {
 int g_gatherChunks = 0;
 int g_bandStride = 0, g_bandOffset = 0;
-int g_gatherMinBlocks = 3;
+int g_gatherMinBlocks = 0;   // 0 = per-mode default (shaft: 4 blocks/SM, packet: 3)
 int g_splatGroup = 0;
 int g_bvhLeafMax = BVH_LEAF_MAX;
 int g_shaftLeafMax = 2;

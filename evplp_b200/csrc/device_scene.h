@@ -359,6 +359,12 @@ __device__ inline bool trace_any_warp(const DevScene& sc, bool active, V3 org, V
     return active && !open;
 }
 
+// Values the compiler must keep in a register instead of re-deriving them inside the traversal loop
+// (it otherwise rematerialises selects / shared-window addresses on every node visit).
+__device__ __forceinline__ int opaque(int x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ float opaque(float x) { asm volatile("" : "+f"(x)); return x; }
+
 // ---- shaft traversal of the 32-wide hierarchy ---------------------------------------------------
 // All 32 shadow rays of a warp start at the same point (the VPL) and end inside the warp's pixel
 // tile, so they lie in the shaft  S(t) = vpl + t * ([tileLo, tileHi] - vpl),  t in [tmin, tmax]
@@ -409,8 +415,9 @@ __device__ __forceinline__ Shaft make_shaft(V3 apex, V3 tileLo, V3 tileHi) {
     s.ilx = il[0]; s.ily = il[1]; s.ilz = il[2]; s.ihx = ih[0]; s.ihy = ih[1]; s.ihz = ih[2];
     s.signs = sg;
     s.sorted = sorted;
-    s.nOffX = nOff[0]; s.nOffY = nOff[1]; s.nOffZ = nOff[2]; s.fOffX = fOff[0]; s.fOffY = fOff[1]; s.fOffZ = fOff[2];
-    s.nix = ni[0]; s.niy = ni[1]; s.niz = ni[2]; s.fix = fi[0]; s.fiy = fi[1]; s.fiz = fi[2];
+    s.nOffX = opaque(nOff[0]); s.nOffY = opaque(nOff[1]); s.nOffZ = opaque(nOff[2]);
+    s.fOffX = opaque(fOff[0]); s.fOffY = opaque(fOff[1]); s.fOffZ = opaque(fOff[2]);
+    s.nix = opaque(ni[0]); s.niy = opaque(ni[1]); s.niz = opaque(ni[2]); s.fix = opaque(fi[0]); s.fiy = opaque(fi[1]); s.fiz = opaque(fi[2]);
     return s;
 }
 
@@ -430,53 +437,60 @@ __device__ __forceinline__ bool shaft_overlap(const Shaft& s, float blx, float b
 }
 
 // Returns per lane whether its ray (org = shaft apex, dir) is occluded.  Must be called by all 32 lanes.
+// stackBase / candBase are shared-window byte addresses of the warp's stack (BVH_STACK words) and candidate list
+// (SHAFT_CAND words); laneOff = lane index (node rows are indexed base + node * 224 + row offset + lane, in floats).
 __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 org, V3 dir, float tmin, float tmax, const Shaft& sh,
-                                            uint32_t* warpStack /* BVH_STACK entries */, uint32_t* cand /* SHAFT_CAND entries */,
+                                            uint32_t stackBase, uint32_t candBase, uint32_t* warpStack,
                                             int candMax /* more candidate leaves than this => per-ray packet traversal */, int* overflow,
                                             unsigned* counters /* [0] fallbacks [1] node visits [2] candidate leaves (per warp) */) {
     const unsigned full = 0xffffffffu;
     if (sc.numShaftNodes == 0 || !__any_sync(full, active)) return false;
-    const int lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
-    int sp = 0, cn = 0;
+    const float* base = reinterpret_cast<const float*>(sc.shaftNodes);
+    constexpr uint32_t NODE_F = sizeof(ShaftNode) / 4;  // floats per node
+    uint32_t sp = stackBase, cp = candBase;
+    const uint32_t spEnd = stackBase + 4u * BVH_STACK, cpEnd = candBase + 4u * (uint32_t)candMax;
     uint32_t cur = 0;
     bool fallback = false;
     while (true) {
-        const ShaftNode* nd = sc.shaftNodes + cur;
         counters[1]++;
-        const uint32_t word = __ldg(&nd->child[lane]);
+        const uint32_t idx = cur * NODE_F + lane;
+        const uint32_t word = __float_as_uint(__ldg(base + idx + 6 * SHAFT_WIDTH));
         bool hit;
         if (sh.sorted) {
-            const float* row = reinterpret_cast<const float*>(nd) + lane;
-            const float tnx = (__ldg(row + sh.nOffX) - sh.apex.x) * sh.nix, tfx = (__ldg(row + sh.fOffX) - sh.apex.x) * sh.fix;
-            const float tny = (__ldg(row + sh.nOffY) - sh.apex.y) * sh.niy, tfy = (__ldg(row + sh.fOffY) - sh.apex.y) * sh.fiy;
-            const float tnz = (__ldg(row + sh.nOffZ) - sh.apex.z) * sh.niz, tfz = (__ldg(row + sh.fOffZ) - sh.apex.z) * sh.fiz;
+            const float tnx = (__ldg(base + idx + sh.nOffX) - sh.apex.x) * sh.nix, tfx = (__ldg(base + idx + sh.fOffX) - sh.apex.x) * sh.fix;
+            const float tny = (__ldg(base + idx + sh.nOffY) - sh.apex.y) * sh.niy, tfy = (__ldg(base + idx + sh.fOffY) - sh.apex.y) * sh.fiy;
+            const float tnz = (__ldg(base + idx + sh.nOffZ) - sh.apex.z) * sh.niz, tfz = (__ldg(base + idx + sh.fOffZ) - sh.apex.z) * sh.fiz;
             hit = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin)) <= fminf(fminf(tfx, tfy), fminf(tfz, tmax));
         } else {
-            hit = shaft_overlap(sh, __ldg(&nd->lox[lane]), __ldg(&nd->loy[lane]), __ldg(&nd->loz[lane]), __ldg(&nd->hix[lane]),
-                                __ldg(&nd->hiy[lane]), __ldg(&nd->hiz[lane]), tmin, tmax);
+            hit = shaft_overlap(sh, __ldg(base + idx), __ldg(base + idx + SHAFT_WIDTH), __ldg(base + idx + 2 * SHAFT_WIDTH),
+                                __ldg(base + idx + 3 * SHAFT_WIDTH), __ldg(base + idx + 4 * SHAFT_WIDTH), __ldg(base + idx + 5 * SHAFT_WIDTH),
+                                tmin, tmax);
         }
         hit = hit && word != BVH_EMPTY;
         const bool leaf = (word & BVH_LEAF_BIT) != 0u;
         const unsigned mi = __ballot_sync(full, hit && !leaf), ml = __ballot_sync(full, hit && leaf);
-        const int ni = __popc(mi), nl = __popc(ml);
-        if (sp + ni > BVH_STACK || cn + nl > candMax) { fallback = true; break; }
-        if (hit && !leaf) warpStack[sp + __popc(mi & lt)] = word;
-        if (hit && leaf) cand[cn + __popc(ml & lt)] = word;
-        sp += ni; cn += nl;
+        const uint32_t spNew = sp + 4u * (uint32_t)__popc(mi), cpNew = cp + 4u * (uint32_t)__popc(ml);
+        if (spNew > spEnd || cpNew > cpEnd) { fallback = true; break; }
+        if (hit && !leaf) st_shared_u32(sp + 4u * (uint32_t)__popc(mi & lt), word);
+        if (hit && leaf) st_shared_u32(cp + 4u * (uint32_t)__popc(ml & lt), word);
+        sp = spNew; cp = cpNew;
         __syncwarp();
-        if (sp == 0) break;
-        cur = warpStack[--sp];
+        if (sp == stackBase) break;
+        sp -= 4u;
+        cur = ld_shared_u32(sp);
     }
     if (fallback) {  // fat shaft (tile across a depth edge) or cluttered region: per-ray packet traversal
         counters[0]++;
         __syncwarp();
         return trace_any_warp(sc, active, org, dir, tmin, tmax, warpStack, overflow);
     }
-    counters[2] += (unsigned)cn;
+    const uint32_t cn = (cp - candBase) >> 2;
+    counters[2] += cn;
     bool occ = false;
-    for (int k = 0; k < cn; k++) {
-        const uint32_t w = cand[k];
+    for (uint32_t k = 0; k < cn; k++) {
+        const uint32_t w = ld_shared_u32(candBase + 4u * k);
         const uint32_t first = bvh_leaf_first(w), count = bvh_leaf_count(w);
         const float4* tp = sc.triLeaf + 4 * (size_t)first;
         for (uint32_t j = 0; j < count; j++, tp += 4) {

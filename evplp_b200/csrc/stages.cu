@@ -247,6 +247,8 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     __shared__ uint32_t cands[SHAFT ? GATHER_WARPS : 1][SHAFT_CAND];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* batch = batchAll[warp];
+    const uint32_t stackBase = opaque((uint32_t)__cvta_generic_to_shared(stacks[warp]));
+    const uint32_t candBase = opaque((uint32_t)__cvta_generic_to_shared(cands[SHAFT ? warp : 0]));
     const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = gp.y0 + (blockIdx.y * gp.bandStride + gp.bandOffset) * 16 + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = x < gp.x1 && y < gp.y1;
@@ -295,7 +297,7 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
             bool occluded;
             if (SHAFT) {
                 const Shaft sh = make_shaft(vpos, tileLo, tileHi);
-                occluded = trace_any_warp_shaft(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stacks[warp], cands[warp], gp.shaftCandMax, &ovf, shaftCnt);
+                occluded = trace_any_warp_shaft(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stackBase, candBase, stacks[warp], gp.shaftCandMax, &ovf, shaftCnt);
                 shaftSteps += __any_sync(0xffffffffu, active) ? 1u : 0u;
             } else {
                 occluded = trace_any_warp(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
@@ -952,7 +954,13 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     }
     c->stageBegin(ST_GATHER);
     if (g_gatherMode == 1) {
-        gather_vpl_kernel<3, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+        const int mb = g_gatherMinBlocks ? g_gatherMinBlocks : 4;  // measured: 64 registers / 4 blocks per SM wins by 5 % here
+        if (mb == 2)
+            gather_vpl_kernel<2, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+        else if (mb == 4)
+            gather_vpl_kernel<4, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+        else
+            gather_vpl_kernel<3, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
     } else {
         switch (g_gatherMinBlocks) {
             case 2: gather_vpl_kernel<2, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
