@@ -317,12 +317,12 @@ def run_gpu(args):
             "ms_per_iteration": sec * 1e3 / args.steps,
             "stage_ms_per_step_rank0": {"gbuffer": stage_ms[0] / args.steps, "light_trace": stage_ms[1] / args.steps,
                                         "vpl_gather": stage_ms[2] / args.steps, "photon_splat": stage_ms[3] / args.steps},
-            "roofline": {"kernel": "gather_vpl_kernel", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+            "roofline": {"kernel": "gather_vpl_kernel<4, true> (shaft gather)", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": ach / fp32_peak, "traffic": None,
                          "note": f"{FLOP_PER_PAIR:.0f} algorithmic FP32 flop per pair (SURVEY 8d) x pairs / gather kernel time; peak = "
                                  f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz ({how} clock); the kernel is shadow-ray traversal bound, "
-                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v4_ncu_full_summary.txt: 67 % of peak "
-                                 "instruction issue, ALU pipe 42 %, FMA pipe 32 %, DRAM 0.01 %)"},
+                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v7_shaft_ncu_full_summary.txt: 64 % of peak "
+                                 "instruction issue, ALU pipe 47 %, FMA pipe 24 %, DRAM 0.02 %)"},
             "roofline_splat": {"kernel": "splat_prepare + splat_fill + splat_tile_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": None,
                                "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}"},
