@@ -231,6 +231,7 @@ struct GatherParams {
     unsigned numChunks;  // VPL list split over gridDim.z
     float vslRadius, vslInvPiRadius2;
     unsigned numLightPaths, numVplLightPaths, B1;
+    int shaftMode;               // 1 = shaft traversal (gather_mode option)
     int shaftCandMax;            // shaft gather: candidate leaves beyond which a (warp, VPL) step falls back to the packet traversal
     int bandStride, bandOffset;  // this launch owns the 16-row bands b = bandOffset (mod bandStride) of the tile (multi-GPU interleave)
 };
@@ -471,9 +472,12 @@ gather_vsl_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ ski
                   const uint32_t* __restrict__ vplCount, long long* __restrict__ acc, DevStats* stats) {
     __shared__ uint32_t sm[kSkipMatrixWords];
     __shared__ uint32_t stacks[GATHER_WARPS][BVH_STACK];
+    __shared__ uint32_t cands[GATHER_WARPS][SHAFT_CAND];
     for (int k = threadIdx.x; k < kSkipMatrixWords; k += blockDim.x) sm[k] = skip[k];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t stackBase = opaque((uint32_t)__cvta_generic_to_shared(stacks[warp]));
+    const uint32_t candBase = opaque((uint32_t)__cvta_generic_to_shared(cands[warp]));
     const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = gp.y0 + (blockIdx.y * gp.bandStride + gp.bandOffset) * 16 + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = x < gp.x1 && y < gp.y1;
@@ -482,6 +486,14 @@ gather_vsl_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ ski
     float gw;
     Surface sf = load_surface(gbuf, n, i, &gw);
     const V3 wi10 = normalize(gp.cameraPosition - sf.pos);
+    // far end of every (VSL -> tile) shaft: bounds of the warp's texel positions (background texels included: the
+    // reference traces their shadow rays too, lighttracing.cu:694-695)
+    V3 tileLo = inside ? sf.pos : v3s(INFINITY), tileHi = inside ? sf.pos : v3s(-INFINITY);
+    for (int o = 16; o > 0; o >>= 1) {
+        tileLo = vmin(tileLo, v3(__shfl_xor_sync(0xffffffffu, tileLo.x, o), __shfl_xor_sync(0xffffffffu, tileLo.y, o), __shfl_xor_sync(0xffffffffu, tileLo.z, o)));
+        tileHi = vmax(tileHi, v3(__shfl_xor_sync(0xffffffffu, tileHi.x, o), __shfl_xor_sync(0xffffffffu, tileHi.y, o), __shfl_xor_sync(0xffffffffu, tileHi.z, o)));
+    }
+    unsigned shaftCnt[3] = {0u, 0u, 0u};
     Xorwow rng = xorwow_seed((uint32_t)i);  // curand_init(launchIndex.y * W + launchIndex.x, rngSeed, 0) -- :711
     xorwow_apply_matrix(rng, sm);
     const uint32_t total = *vplCount;
@@ -494,7 +506,14 @@ gather_vsl_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ ski
         const V3 v12 = vp.pos - sf.pos;
         rays += inside ? 1u : 0u;
         // shadow ray FIRST, before the cosine test (lighttracing.cu:609-614)
-        const bool occluded = trace_any_warp(sc, inside, vp.pos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
+        bool occluded;
+        if (gp.shaftMode) {
+            const Shaft sh = make_shaft(vp.pos, tileLo, tileHi);
+            occluded = trace_any_warp_shaft(sc, inside, vp.pos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stackBase, candBase,
+                                            stacks[warp], gp.shaftCandMax, &ovf, shaftCnt);
+        } else {
+            occluded = trace_any_warp(sc, inside, vp.pos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
+        }
         if (inside && !occluded) result += vsl_shade(gp, sf, wi10, vp, v12, rng);
     }
     if (ovf) stats->stackOverflow = 1;
@@ -889,6 +908,7 @@ static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
     g.numChunks = 1;
     g.vslRadius = P.vslRadius; g.vslInvPiRadius2 = P.vslInvPiRadius2;
     g.numLightPaths = P.numLightPaths; g.numVplLightPaths = P.numVplLightPaths; g.B1 = P.numPhotonsPerLightPath;
+    g.shaftMode = g_gatherMode == 2 ? 1 : 0;  // VSL gather: sampling-bound, the shaft brings nothing there (measured); opt-in with gather_mode = 2
     g.shaftCandMax = g_shaftCandMax < 1 ? 1 : (g_shaftCandMax > SHAFT_CAND ? SHAFT_CAND : g_shaftCandMax);
     g.bandStride = g_bandStride > 0 ? g_bandStride : 1;
     g.bandOffset = g_bandStride > 0 ? g_bandOffset : 0;
@@ -953,7 +973,7 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         c->launches++;
     }
     c->stageBegin(ST_GATHER);
-    if (g_gatherMode == 1) {
+    if (g_gatherMode >= 1) {
         const int mb = g_gatherMinBlocks ? g_gatherMinBlocks : 4;  // measured: 64 registers / 4 blocks per SM wins by 5 % here
         if (mb == 2)
             gather_vpl_kernel<2, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);

@@ -201,7 +201,9 @@ def test_vpl_gather_accumulates_and_tiles(rig):
     assert np.array_equal(vpl, eacc)
 
 
-def test_vsl_gather_bit_exact(rig):
+@pytest.mark.parametrize("gather_mode", [0, 2])
+def test_vsl_gather_bit_exact(rig, gather_mode):
+    rig.dev.set_option("gather_mode", gather_mode)
     P = rig.params(mis_mode=0, accumulate=False, num_vpl_paths=24)
     planes, prims, rec = _setup_iteration(rig, P)
     exp, cnt = rig.orc.vpl_gather(P, W, H, planes, prims, rec, capi.GATHER_VSL)
@@ -211,6 +213,7 @@ def test_vsl_gather_bit_exact(rig):
     rig.dev.reset_stats()
     rig.dev.vpl_gather(capi.GATHER_VSL)
     vpl, _, _ = rig.dev.download_accum()
+    rig.dev.set_option("gather_mode", 1)
     assert np.array_equal(vpl, eacc)
     st = rig.dev.stats()
     assert st.gatherPairs == int(cnt[0]) and st.shadowRays == int(cnt[1])
