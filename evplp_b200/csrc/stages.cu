@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128) light_trace_kernel(DevScene sc, const uin
 }
 
 // ------------------------------------------------------------------ VPL gather ----------
-constexpr int GATHER_BATCH = 32;    // VPL records staged per warp and shared-memory batch
+constexpr int GATHER_BATCH = 16;    // VPL records staged per warp and shared-memory batch
 constexpr int GATHER_WARPS = 8;
 
 struct GatherParams {

@@ -361,7 +361,7 @@ protected:
     }
     int mDevice = 0, mBaseGatherMode = EVPLP_GATHER_VPL, mRank = 0, mWorldSize = 1;
     EPartition mPartition = PartitionIterations;
-    uint64_t mMaxPathsPerTrace = 8ull << 20;  // 8 Mi paths = 3.2 GB of records per chunk
+    uint64_t mMaxPathsPerTrace = 32ull << 20;  // 32 Mi paths = 12.9 GB of records per chunk (180 GB of HBM per GPU)
     void* mNcclComm = nullptr;
     bool mWriteOutputs = true;
     evplp_handle mHandle = nullptr;
