@@ -255,6 +255,78 @@ __global__ void collapse_kernel(const uint32_t* __restrict__ queueIn, const uint
     }
 }
 
+// Warp-cooperative collapse for the 32-wide hierarchy: one warp per work item, lane k owns candidate k.  Every round the
+// warp opens the expandable candidate with the largest box (arg-max by shuffles); the node is written with one child
+// per lane (coalesced 128-byte rows).
+__global__ void collapse32_kernel(const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ counters, int level,
+                                  uint32_t* __restrict__ queueOut, uint32_t* countersOut,
+                                  const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                  const int32_t* __restrict__ rangeFirst, const int32_t* __restrict__ rangeLast,
+                                  const float* __restrict__ nodeBounds, const float* __restrict__ primLo,
+                                  const float* __restrict__ primHi, const uint32_t* __restrict__ sorted, float pad, int leafMax,
+                                  ShaftNode* __restrict__ nodes) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t numIn = counters[1 + (level & 1)];
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= numIn) return;  // whole warp
+    const int bin = (int)queueIn[2 * (size_t)w];
+    const uint32_t slot = queueIn[2 * (size_t)w + 1];
+    const int NONE = 0x7fffffff;
+    int cand = lane == 0 ? left[bin] : lane == 1 ? right[bin] : NONE;
+    int nc = 2;
+    while (nc < SHAFT_WIDTH) {
+        // key = half-area of expandable candidates, -1 otherwise
+        float key = -1.f;
+        if (cand != NONE && cand >= 0 && rangeLast[cand] - rangeFirst[cand] + 1 > leafMax) key = half_area(nodeBounds + 6 * (size_t)cand);
+        float best = key;
+        int bestLane = lane;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(full, best, o);
+            const int ol = __shfl_xor_sync(full, bestLane, o);
+            if (ok > best || (ok == best && ol < bestLane)) { best = ok; bestLane = ol; }
+        }
+        if (best < 0.f) break;
+        const int c = __shfl_sync(full, cand, bestLane);
+        if (lane == bestLane) cand = left[c];
+        if (lane == nc) cand = right[c];
+        nc++;
+    }
+    ShaftNode& nd = nodes[slot];
+    float b[6] = {BVH_EMPTY_COORD, BVH_EMPTY_COORD, BVH_EMPTY_COORD, BVH_EMPTY_COORD, BVH_EMPTY_COORD, BVH_EMPTY_COORD};
+    uint32_t word = BVH_EMPTY;
+    bool isNode = false;
+    if (cand != NONE) {
+        child_bounds(cand, nodeBounds, primLo, primHi, sorted, b);
+        for (int k = 0; k < 3; k++) { b[k] -= pad; b[3 + k] += pad; }
+        if (cand < 0) {
+            word = bvh_make_leaf((uint32_t)(~cand), 1u);
+        } else {
+            const int cnt = rangeLast[cand] - rangeFirst[cand] + 1;
+            if (cnt <= leafMax) word = bvh_make_leaf((uint32_t)rangeFirst[cand], (uint32_t)cnt);
+            else isNode = true;
+        }
+    }
+    // allocate node slots + queue entries for the child nodes with one atomic pair per warp
+    const unsigned m = __ballot_sync(full, isNode);
+    uint32_t baseIdx = 0, baseQ = 0;
+    if (lane == 0 && m) {
+        baseIdx = atomicAdd(&countersOut[0], (uint32_t)__popc(m));
+        baseQ = atomicAdd(&countersOut[1 + ((level + 1) & 1)], (uint32_t)__popc(m));
+    }
+    baseIdx = __shfl_sync(full, baseIdx, 0);
+    baseQ = __shfl_sync(full, baseQ, 0);
+    if (isNode) {
+        const uint32_t r = (uint32_t)__popc(m & ((1u << lane) - 1u));
+        word = baseIdx + r;
+        queueOut[2 * (size_t)(baseQ + r)] = (uint32_t)cand;
+        queueOut[2 * (size_t)(baseQ + r) + 1] = word;
+    }
+    nd.lox[lane] = b[0]; nd.loy[lane] = b[1]; nd.loz[lane] = b[2];
+    nd.hix[lane] = b[3]; nd.hiy[lane] = b[4]; nd.hiz[lane] = b[5];
+    nd.child[lane] = word;
+}
+
 // Scene with <= BVH_LEAF_MAX triangles: one node, one leaf child.
 template <int W>
 __global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const float* __restrict__ primHi, float pad,
@@ -288,23 +360,35 @@ static cudaError_t run_collapse(EvplpContext* c, WideNodeT<W>* nodes, int leafMa
     uint32_t rootItem[2] = {0u, 0u};
     CK(cudaMemcpyAsync(c->counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->queueA.p, rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, st));
-    uint32_t numIn = 1;
+    // The item count of a level lives on the device; the grids are sized from an upper bound (W x the previous bound, at
+    // most one item per binary internal node) and surplus threads exit, so the host only synchronises every 8 levels.
+    const uint64_t cap = c->numPrims > 1 ? (uint64_t)c->numPrims - 1 : 1;
+    uint64_t bound = 1;
     int level = 0;
-    while (numIn > 0) {
+    while (true) {
         uint32_t* qin = (level & 1) ? c->queueB.p : c->queueA.p;
         uint32_t* qout = (level & 1) ? c->queueA.p : c->queueB.p;
         CK(cudaMemsetAsync(c->counters.p + 1 + ((level + 1) & 1), 0, sizeof(uint32_t), st));
-        collapse_kernel<W><<<(numIn + 63) / 64, 64, 0, st>>>(qin, c->counters.p, level, qout, c->counters.p, c->left.p, c->right.p,
-                                                             c->rangeFirst.p, c->rangeLast.p, c->nodeBounds.p, c->primLo.p,
-                                                             c->primHi.p, c->primIdsSorted.p, c->boxPad, leafMax, nodes);
+        if constexpr (W == SHAFT_WIDTH) {
+            collapse32_kernel<<<(unsigned)((bound + 3) / 4), 128, 0, st>>>(qin, c->counters.p, level, qout, c->counters.p, c->left.p, c->right.p,
+                                                                        c->rangeFirst.p, c->rangeLast.p, c->nodeBounds.p, c->primLo.p,
+                                                                        c->primHi.p, c->primIdsSorted.p, c->boxPad, leafMax, nodes);
+        } else {
+            collapse_kernel<W><<<(unsigned)((bound + 63) / 64), 64, 0, st>>>(qin, c->counters.p, level, qout, c->counters.p, c->left.p, c->right.p,
+                                                                          c->rangeFirst.p, c->rangeLast.p, c->nodeBounds.p, c->primLo.p,
+                                                                          c->primHi.p, c->primIdsSorted.p, c->boxPad, leafMax, nodes);
+        }
         c->launches++;
-        uint32_t cnt[3];
-        CK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        numIn = cnt[1 + ((level + 1) & 1)];
-        *numNodesOut = (int)cnt[0];
+        bound = bound * W < cap ? bound * W : cap;
         level++;
-        if (level > 4096) { if (err) *err = "wide collapse did not terminate"; return cudaErrorUnknown; }
+        if (level % 8 == 0 || level > 4096) {
+            uint32_t cnt[3];
+            CK(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            *numNodesOut = (int)cnt[0];
+            if (cnt[1 + (level & 1)] == 0) break;  // the queue the next level would read is empty
+            if (level > 4096) { if (err) *err = "wide collapse did not terminate"; return cudaErrorUnknown; }
+        }
     }
     return cudaGetLastError();
 }
