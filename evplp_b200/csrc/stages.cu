@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(DevScene sc, CamParams cam
 }
 
 // ------------------------------------------------------------------ light tracing -------
-__global__ void __launch_bounds__(128) light_trace_kernel(DevScene sc, const uint32_t* __restrict__ skip,
+__global__ void __launch_bounds__(128, 8) light_trace_kernel(DevScene sc, const uint32_t* __restrict__ skip,
                                                           EvplpRecord* __restrict__ records, uint32_t firstPath,
                                                           uint32_t numPaths, uint32_t B1, DevStats* stats) {
     __shared__ uint32_t sm[kSkipMatrixWords];
@@ -977,6 +977,8 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         const int mb = g_gatherMinBlocks ? g_gatherMinBlocks : 4;  // measured: 64 registers / 4 blocks per SM wins by 5 % here
         if (mb == 2)
             gather_vpl_kernel<2, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+        else if (mb == 5)
+            gather_vpl_kernel<5, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
         else if (mb == 4)
             gather_vpl_kernel<4, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
         else
