@@ -313,7 +313,10 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "partition": f"iterations round-robin over {world} GPU(s), one all-reduce of the "
                        "int64 accumulation layers per timed batch", "l2": "inputs larger than L2: per iteration 133 MB G-buffer + "
                        "115 MB records + 100 MB accumulators are rewritten/re-read"},
+            # photons / fragments per second of the WHOLE step (the gather takes 99.9 % of it) and of the splat stage alone
             "splatted_photons_per_s": photons / sec, "splat_fragments_per_s": frags / sec, "shadow_rays_per_s": rays / sec,
+            "splat_stage_photons_per_s": my_photons / splat_s * world, "light_trace_stage_paths_per_s":
+            PHOTONFAM["numLightPaths"] * args.steps / max(stage_ms[1] / 1e3, 1e-9) * world,
             "ms_per_iteration": sec * 1e3 / args.steps,
             "stage_ms_per_step_rank0": {"gbuffer": stage_ms[0] / args.steps, "light_trace": stage_ms[1] / args.steps,
                                         "vpl_gather": stage_ms[2] / args.steps, "photon_splat": stage_ms[3] / args.steps},
