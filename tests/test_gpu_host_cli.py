@@ -61,3 +61,51 @@ def test_cli_render_writes_the_reference_outputs(tmp_path, variant):
         assert not vpl.any() and photon.any()      # numVplLightPaths 0 disables the gather (rtcomphoton.h:200-203)
     if variant == "vsl":
         assert vpl.any() and not photon.any()      # radiusPercentage 0: no splat fragments
+
+
+def _fam(**kw):
+    fam = {"rngOffset": 0, "numMaxIteration": -1, "timeLimitMs": -1.0, "frameMode": "accumulate", "combinedFilename": "a.pfm",
+           "weightedPhotonFilename": "b.pfm", "weightedVplFilename": "c.pfm", "statFilename": "s.json", "useJitter": False, "useStat": False,
+           "numLightPaths": 20000, "numVplLightPaths": 32, "numMaxBounces": 3, "radiusPercentage": 0.01, "misMode": "geometryClamp",
+           "clampingCoeff": 0.05, "DoProgressive": False}
+    fam.update(kw)
+    return fam
+
+
+def test_cleareveryframe_keeps_only_the_last_iteration():
+    """frameMode cleareveryframe (doAccumulate = 0, lighttracing.cu:378; glClear per frame, rtcomphoton.h:978-981)."""
+    hs = HA.HostScene.generate("livingroom", 3, 2, 320 / 180)
+    a = HA.Technique(hs, _fam(frameMode="cleareveryframe"), 320, 180)
+    for _ in range(3):
+        a.iterate()                                   # iterations use rngSeed 0, 1, 2; the buffers are cleared each time
+    img_a = a.final(1.0, 1.0, 1.0)
+    a.close()
+    b = HA.Technique(hs, _fam(rngOffset=2), 320, 180)  # one accumulated iteration with rngSeed 2
+    b.iterate()
+    img_b = b.final(1.0, 1.0, 1.0)
+    b.close()
+    assert img_a.any() and np.array_equal(img_a, img_b)
+
+
+def test_lvc_technique_runs_through_the_host_class(tmp_path):
+    """RtLvcComPhoton ("lvcphotonfam", main.cpp:116-120): per-pixel window of light paths (lvclighttracing.cu:348-387)."""
+    d = str(tmp_path)
+    HA.export_scene("livingroom", d, seed=3, detail=2, res_x=160, res_y=90)
+    jpath = os.path.join(d, "livingroom_ours.json")
+    j = json.load(open(jpath))
+    fam = j.pop("photonfam")
+    fam.update(numMaxIteration=2, numLightPaths=4096, numVplLightPaths=16, timeLimitMs=600000.0)
+    j["lvcphotonfam"] = fam
+    json.dump(j, open(jpath, "w"))
+    r = subprocess.run([EXE, jpath], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "lvcphotonfam: 2 iterations" in r.stdout
+    comb = _read_pfm_rows(os.path.join(d, fam["combinedFilename"]))
+    hs = HA.HostScene.load(jpath)
+    t = HA.Technique(hs, fam, 160, 90, lvc=True)
+    for _ in range(2):
+        t.iterate()
+    half = np.float32(0.5)
+    exp = (t.final(0.0, 0.0, 1.0) + t.final(1.0, 0.0, 0.0) * half) + t.final(0.0, 1.0, 0.0) * half
+    t.close()
+    assert comb.mean() > 1e-4 and np.array_equal(comb, exp)
