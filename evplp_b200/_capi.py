@@ -100,6 +100,7 @@ SYMBOLS = {
     "evplp_gbuffer": (C.c_int, [_P]),
     "evplp_light_trace": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
     "evplp_vpl_gather": (C.c_int, [_P, C.POINTER(Tile), C.c_int]),
+    "evplp_path_trace": (C.c_int, [_P, C.POINTER(Tile), C.c_uint32]),
     "evplp_photon_splat": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.POINTER(Tile)]),
     "evplp_light_pass": (C.c_int, [_P]),
     "evplp_reduce": (C.c_int, [_P, _P]),

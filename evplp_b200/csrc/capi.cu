@@ -307,6 +307,19 @@ int evplp_vpl_gather(evplp_handle c, const EvplpTile* tile, int gatherMode) {
     return EVPLP_OK;
 }
 
+int evplp_path_trace(evplp_handle c, const EvplpTile* tile, uint32_t maxBounces) {
+    NEED(c != nullptr, "evplp_path_trace: NULL handle");
+    NEED(c->bvhBuilt && c->paramsSet && c->gbufValid, "evplp_path_trace: needs evplp_build_bvh, evplp_set_params and a G-buffer first");
+    CU(cudaSetDevice(c->device));
+    EvplpTile t;
+    int rc = tile_of(c, tile, &t);
+    if (rc) return rc;
+    rc = ensure_skip_matrix(c, c->params.rngSeed);
+    if (rc) return rc;
+    CU(launch_path_trace(c, t, maxBounces));
+    return EVPLP_OK;
+}
+
 int evplp_photon_splat(evplp_handle c, uint64_t firstRecord, uint64_t numRecords, const EvplpTile* tile) {
     NEED(c != nullptr, "evplp_photon_splat: NULL handle");
     NEED(c->paramsSet && c->gbufValid, "evplp_photon_splat: needs evplp_set_params and a G-buffer first");

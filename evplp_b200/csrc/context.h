@@ -115,6 +115,7 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err);
 cudaError_t launch_gbuffer(EvplpContext* c);
 cudaError_t launch_light_trace(EvplpContext* c, uint32_t rngSeed, uint32_t firstPath, uint32_t numPaths);
 cudaError_t launch_gather(EvplpContext* c, EvplpTile tile, int mode);
+cudaError_t launch_path_trace(EvplpContext* c, EvplpTile tile, uint32_t maxBounces);
 cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numRecords, EvplpTile tile);
 cudaError_t launch_light_pass(EvplpContext* c);
 cudaError_t launch_resolve(EvplpContext* c, float vplScale, float photonScale, float lightScale, int gamma);

@@ -146,6 +146,30 @@ EVPLP_HD V3 phong_sample(V3* out, float* pdfW, V3 in, V3 normal, V3 phongReflect
     return det_div(phongExponent + 2.0f, phongExponent + 1.0f) * cosNormal * phongReflectance;
 }
 
+// rtmaterial.cuh:104-111 (the CUDA PhongEval: threshold 1e-6 and the Ks.x test; the GLSL one differs, see below)
+EVPLP_HD V3 phong_eval(V3 out, V3 in, V3 normal, V3 ks, float e) {
+    V3 reflectVec = reflect(-in, normal);
+    float dotWrWo = det_max(dot(out, reflectVec), 0.0f);
+    if (dotWrWo <= 0.000001f || ks.x <= 0.000001f) return v3s(0.0f);
+    return ks * (e + 2.0f) * det_powf(dotWrWo, e) * (kInvPi) * 0.5f;
+}
+// rtmaterial.cuh:30-38
+EVPLP_HD float geometry_term(V3 n1, V3 n2, V3 v12) {
+    const float c1 = det_max(dot(n1, v12), 0.f);
+    const float c2 = det_max(-dot(n2, v12), 0.f);
+    const float d2 = dot(v12, v12);
+    return det_div(c1 * c2, d2 * d2);
+}
+// pathtracing.cu:85-95
+EVPLP_HD float pdf_w2a(V3 n2, V3 v12) {
+    V3 nv12 = normalize(v12);
+    return det_div(det_max(-dot(n2, nv12), 0.f), dot(v12, v12));
+}
+// pathtracing.cu:49-52 (quirk kept: the probability is never below 0.98 and may exceed 1)
+EVPLP_HD float pt_russian_prob(V3 throughput) {
+    return det_max(det_max(throughput.x, 0.98f), det_max(throughput.y, throughput.z));
+}
+
 // rtmath.cuh:23-28
 EVPLP_HD void square_to_barycentric(float* beta, float* gamma, float x, float y) {
     const float sqrtX = det_sqrtf(x);

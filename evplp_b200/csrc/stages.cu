@@ -114,6 +114,27 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(DevScene sc, CamParams cam
     gprim[i] = hit.prim;
 }
 
+// LightSample -- rtlightsource.cuh:24-80: triangle by lower-bound search in the area CDF, uniform point on it;
+// returns areaLightIntensity.rgb * area (pdf = 1 / area).  Three uniforms, drawn in order.
+__device__ __forceinline__ V3 light_sample(const DevScene& sc, V3* position, V3* normal, Xorwow& rng) {
+    float randNum = xorwow_uniform(rng);
+    unsigned count = (unsigned)sc.lightCount, first = 0;
+    while (count > 0) {
+        unsigned step = count / 2;
+        unsigned it = first + step;
+        if (sc.lightCdf[it] < randNum) { first = it + 1; count -= step + 1; } else { count = step; }
+    }
+    const size_t prim = (size_t)sc.lightFirst + first;
+    const V3 pos1 = ld3(sc.triVerts[3 * prim]), pos2 = ld3(sc.triVerts[3 * prim + 1]), pos3 = ld3(sc.triVerts[3 * prim + 2]);
+    float bx = xorwow_uniform(rng);
+    float by = xorwow_uniform(rng);
+    float beta, gamma;
+    square_to_barycentric(&beta, &gamma, bx, by);
+    *position = pos1 * beta + pos2 * gamma + pos3 * (1.0f - gamma - beta);
+    *normal = normalize(cross(pos2 - pos1, pos3 - pos1));
+    return v3(sc.lightIntensity[0], sc.lightIntensity[1], sc.lightIntensity[2]) * sc.lightArea;
+}
+
 // ------------------------------------------------------------------ light tracing -------
 __global__ void __launch_bounds__(128, 8) light_trace_kernel(DevScene sc, const uint32_t* __restrict__ skip,
                                                           EvplpRecord* __restrict__ records, uint32_t firstPath,
@@ -129,26 +150,8 @@ __global__ void __launch_bounds__(128, 8) light_trace_kernel(DevScene sc, const 
     Xorwow rng = xorwow_seed(firstPath + i);
     xorwow_apply_matrix(rng, sm);
 
-    // LightSample -- rtlightsource.cuh:24-80
-    V3 position, normal, flux;
-    {
-        float randNum = xorwow_uniform(rng);
-        unsigned count = (unsigned)sc.lightCount, first = 0;
-        while (count > 0) {
-            unsigned step = count / 2;
-            unsigned it = first + step;
-            if (sc.lightCdf[it] < randNum) { first = it + 1; count -= step + 1; } else { count = step; }
-        }
-        const size_t prim = (size_t)sc.lightFirst + first;
-        const V3 pos1 = ld3(sc.triVerts[3 * prim]), pos2 = ld3(sc.triVerts[3 * prim + 1]), pos3 = ld3(sc.triVerts[3 * prim + 2]);
-        float bx = xorwow_uniform(rng);
-        float by = xorwow_uniform(rng);
-        float beta, gamma;
-        square_to_barycentric(&beta, &gamma, bx, by);
-        position = pos1 * beta + pos2 * gamma + pos3 * (1.0f - gamma - beta);
-        normal = normalize(cross(pos2 - pos1, pos3 - pos1));
-        flux = v3(sc.lightIntensity[0], sc.lightIntensity[1], sc.lightIntensity[2]) * sc.lightArea;
-    }
+    V3 position, normal;
+    V3 flux = light_sample(sc, &position, &normal, rng);
     V3 direction;
     float pdfW;
     V3 att = phong_sample(&direction, &pdfW, normal, normal, v3s(1.0f), sc.lightIntensity[3], rng);
@@ -577,6 +580,140 @@ gather_lvc_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ ski
     for (int c = 0; c < 3; c++) acc[i * 3 + c] = gp.doAccumulate ? acc[i * 3 + c] + q[c] : q[c];
 }
 
+// ------------------------------------------------------------------ path tracing (RtPt2) --
+// pathtracing.cu:112-377: unidirectional path tracer from the G-buffer first hit with next-event estimation and
+// balance-heuristic MIS -- the reference's own ground-truth generator.  One thread per pixel,
+// per-pixel XORWOW stream curand_init(pixel, rngSeed, 0); per-lane traversal (paths are incoherent).
+__global__ void __launch_bounds__(128) path_trace_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ skip,
+                                                         const float4* __restrict__ gbuf, unsigned maxBounces,
+                                                         long long* __restrict__ acc, DevStats* stats) {
+    __shared__ uint32_t sm[kSkipMatrixWords];
+    for (int k = threadIdx.x; k < kSkipMatrixWords; k += blockDim.x) sm[k] = skip[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = gp.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (!(x < gp.x1 && y < gp.y1)) return;
+    const size_t n = (size_t)gp.W * gp.H;
+    const size_t i = (size_t)y * gp.W + x;
+    float gw;
+    const Surface sf = load_surface(gbuf, n, i, &gw);
+    V3 result = v3s(0.0f);
+    int ovf = 0;
+    unsigned long long rays = 0;
+    const float lightExp = sc.lightIntensity[3];
+    const float lightPdf = det_div(1.f, sc.lightArea);
+    if (gw != 0.0f) {
+        Xorwow rng = xorwow_seed((uint32_t)i);
+        xorwow_apply_matrix(rng, sm);
+        // ---- pathTraceSimple, first bounce (:232-305)
+        const V3 cameraVec = normalize(sf.pos - gp.cameraPosition);
+        V3 position = sf.pos, direction = v3s(0.f), attenuation = v3s(1.0f);
+        float brdfPdfW = 0.f;
+        bool alive = true;
+        {
+            V3 lightPosition, lightNormal;
+            V3 lightValue = light_sample(sc, &lightPosition, &lightNormal, rng);
+            V3 toLight = lightPosition - position;
+            V3 toLightNorm = normalize(toLight);
+            rays++;
+            const bool hit = trace_any(sc, lightPosition, -toLight, 0.0001f, 1.0f - 0.0001f, &ovf);
+            float maxLambert = max_color(sf.kd), maxPhong = max_color(sf.ks);
+            float pSel = det_div(maxLambert, maxPhong + maxLambert);
+            if (maxLambert + maxPhong <= 0.000001f) {
+                alive = false;
+            } else {
+                float chooseMaterial = det_min(xorwow_uniform(rng), 0.999999f);
+                if (chooseMaterial < pSel) {
+                    if (!hit) {
+                        float brdfPdf = lambert_pdf_a(sf.normal, lightNormal, toLight);
+                        float weight = balance_heuristic(lightPdf, brdfPdf);
+                        result += weight * lightValue * (sf.kd * kInvPi) * geometry_term(sf.normal, lightNormal, toLight) / pSel *
+                                  phong_eval_f(lightNormal, -toLightNorm, lightNormal, lightExp);
+                    }
+                    attenuation *= lambert_sample(&direction, &brdfPdfW, sf.normal, sf.kd, rng) / pSel;
+                } else {
+                    if (!hit) {
+                        float brdfPdf = phong_pdf_a(sf.normal, lightNormal, toLight, -cameraVec, sf.ks, sf.exponent);
+                        float weight = balance_heuristic(lightPdf, brdfPdf);
+                        result += weight * lightValue * phong_eval(-cameraVec, toLightNorm, sf.normal, sf.ks, sf.exponent) *
+                                  geometry_term(sf.normal, lightNormal, toLight) / (1.0f - pSel) *
+                                  phong_eval_f(lightNormal, -toLightNorm, lightNormal, lightExp);
+                    }
+                    attenuation *= phong_sample(&direction, &brdfPdfW, -cameraVec, sf.normal, sf.ks, sf.exponent, rng) / (1.0f - pSel);
+                }
+            }
+        }
+        // ---- bounces: rtTrace + rtMaterialClosestHit (:112-218, 307-318)
+        for (unsigned b = 0; alive && b < maxBounces; b++) {
+            const bool last = (b == maxBounces - 1);
+            rays++;
+            const RayHit h = trace_closest(sc, position, direction, 0.00001f, 1e27f, &ovf);
+            if (h.prim < 0) break;  // no miss program: nothing more is added
+            const DevMaterial& mat = sc.mats[h.mat];
+            const V3 geometryNormal = normalize(h.n);
+            const V3 worldGeometryNormal = normalize(geometryNormal);
+            const V3 ffNormal = faceforward(worldGeometryNormal, -direction, worldGeometryNormal);
+            const V3 nextPosition = position + h.t * direction;
+            if (dot(geometryNormal, direction) > 0.f) break;  // result = 0, done
+            if (mat.lightIntensity[0] > 0.01f) {             // hit the light: MIS against the light sampling of the previous vertex
+                float brdfPdfA = brdfPdfW * pdf_w2a(ffNormal, nextPosition - position);
+                float weight = balance_heuristic(brdfPdfA, lightPdf);
+                result += weight * attenuation * phong_eval_f(geometryNormal, normalize(position - nextPosition), geometryNormal, mat.lightIntensity[3]) *
+                          v3(mat.lightIntensity[0], mat.lightIntensity[1], mat.lightIntensity[2]);
+                break;
+            }
+            if (last) break;  // last bounce: no next-event estimation
+            V3 lightPosition, lightNormal;
+            V3 lightValue = light_sample(sc, &lightPosition, &lightNormal, rng);
+            V3 toLight = lightPosition - nextPosition;
+            V3 toLightNorm = normalize(toLight);
+            rays++;
+            const bool hit = trace_any(sc, lightPosition, -toLight, 0.00001f, 0.99999f, &ovf);
+            const float2 t0 = sc.triUV[3 * (size_t)h.prim], t1 = sc.triUV[3 * (size_t)h.prim + 1], t2 = sc.triUV[3 * (size_t)h.prim + 2];
+            const float w0 = 1.0f - h.beta - h.gamma;
+            const float u = t1.x * h.beta + t2.x * h.gamma + t0.x * w0;
+            const float v = t1.y * h.beta + t2.y * h.gamma + t0.y * w0;
+            Texel4 tl = tex_fetch(mat.lambert, sc.texPool, u, v);
+            Texel4 tp = tex_fetch(mat.phong, sc.texPool, u, v);
+            Texel4 te = tex_fetch(mat.exponent, sc.texPool, u, v);
+            const V3 kd = v3(tl.x, tl.y, tl.z), ks = v3(tp.x, tp.y, tp.z);
+            const float phongExponent = te.x;
+            float maxLambert = max_color(kd), maxPhong = max_color(ks);
+            if (maxLambert + maxPhong <= 0.000001f) break;
+            float pSel = det_div(maxLambert, maxPhong + maxLambert);
+            float chooseMaterial = det_min(xorwow_uniform(rng), 0.999999f);
+            const V3 toPrev = normalize(position - nextPosition);
+            if (chooseMaterial < pSel) {
+                if (!hit) {
+                    float brdfPdf = lambert_pdf_a(ffNormal, lightNormal, toLight);
+                    float weight = balance_heuristic(lightPdf, brdfPdf);
+                    result += weight * lightValue * (kd * kInvPi) * geometry_term(ffNormal, lightNormal, toLight) * attenuation / pSel *
+                              phong_eval_f(lightNormal, -toLightNorm, lightNormal, lightExp);
+                }
+                attenuation *= lambert_sample(&direction, &brdfPdfW, geometryNormal, kd, rng) / pSel;
+            } else {
+                if (!hit) {
+                    float brdfPdf = phong_pdf_a(ffNormal, lightNormal, toLight, toPrev, ks, phongExponent);
+                    float weight = balance_heuristic(lightPdf, brdfPdf);
+                    result += weight * lightValue * phong_eval(toLightNorm, toPrev, ffNormal, ks, phongExponent) *
+                              geometry_term(ffNormal, lightNormal, toLight) * attenuation / (1.0f - pSel) *
+                              phong_eval_f(lightNormal, -toLightNorm, lightNormal, lightExp);
+                }
+                attenuation *= phong_sample(&direction, &brdfPdfW, toPrev, geometryNormal, ks, phongExponent, rng) / (1.0f - pSel);
+            }
+            float russian = pt_russian_prob(attenuation);
+            if (xorwow_uniform(rng) >= russian) break;
+            position = nextPosition;
+            attenuation /= russian;
+        }
+    }
+    if (ovf) stats->stackOverflow = 1;
+    if (rays) atomicAdd(&stats->closestRays, rays);
+    const long long q[3] = {to_fixed(result.x), to_fixed(result.y), to_fixed(result.z)};
+    for (int c = 0; c < 3; c++) acc[i * 3 + c] = gp.doAccumulate ? acc[i * 3 + c] + q[c] : q[c];
+}
+
 // ------------------------------------------------------------------ photon splat --------
 struct SplatParams {
     SplatUniforms U;
@@ -990,6 +1127,18 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
             default: gather_vpl_kernel<3, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
         }
     }
+    c->stageEnd(ST_GATHER);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_path_trace(EvplpContext* c, EvplpTile t, uint32_t maxBounces) {
+    GatherParams g = gather_params(c, t);
+    const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
+    if (tw <= 0 || th <= 0) return cudaSuccess;
+    dim3 grid((tw + 15) / 16, (th + 7) / 8);
+    c->stageBegin(ST_GATHER);
+    path_trace_kernel<<<grid, 128, 0, c->stream>>>(c->scene(), g, c->skipMatrix.p, c->gbuf.p, maxBounces, c->accVpl.p, c->devStats.p);
     c->stageEnd(ST_GATHER);
     c->launches++;
     return cudaGetLastError();

@@ -66,6 +66,9 @@ class Device:
     def vpl_gather(self, mode=capi.GATHER_VPL, tile=None):
         self._ck(self.lib.evplp_vpl_gather(self.h, self._tile(tile), mode), "evplp_vpl_gather")
 
+    def path_trace(self, max_bounces, tile=None):
+        self._ck(self.lib.evplp_path_trace(self.h, self._tile(tile), max_bounces), "evplp_path_trace")
+
     def photon_splat(self, first_record, num_records, tile=None):
         self._ck(self.lib.evplp_photon_splat(self.h, first_record, num_records, self._tile(tile)), "evplp_photon_splat")
 

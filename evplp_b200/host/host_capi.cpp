@@ -3,6 +3,7 @@
 // render call goes through libevplp_b200.so.
 #include <cstring>
 #include "rtcomphoton.h"
+#include "rtpt2.h"
 #include "scenegen.h"
 
 using namespace evplp_host;
@@ -131,6 +132,33 @@ int evplp_host_technique_final(void* t, float vplScale, float photonScale, float
 
 void evplp_host_technique_destroy(void* t) { delete (HostTechnique*)t; }
 
+// RtPt2 stepped one iteration at a time; `ptJson` is the text of the "pt" object.
+struct HostPt { std::unique_ptr<RtPt2> tech; shared_ptr<RtScene> scene; };
+void* evplp_host_pt_create(void* s, const char* ptJson, int resX, int resY, int device, int rank, int worldSize) {
+    try {
+        HostScene* hs = (HostScene*)s;
+        auto* hp = new HostPt();
+        hp->scene = hs->scene;
+        hp->tech.reset(new RtPt2(device));
+        hp->tech->setPartition(rank, worldSize);
+        hp->tech->setWriteOutputs(false);
+        Vec2 res; res.x = (float)resX; res.y = (float)resY;
+        hp->tech->parse(hp->scene, res, Json::parse(ptJson));
+        hp->tech->setup();
+        return hp;
+    } catch (const std::exception& e) { g_hostErr = e.what(); return nullptr; }
+}
+int evplp_host_pt_iterate(void* t) { GUARD(return ((HostPt*)t)->tech->iterate() ? 1 : 0;) }
+int evplp_host_pt_final(void* t, float ptScale, float lightScale, int gamma, float* hostRGB) {
+    GUARD(
+        FloatImage img = ((HostPt*)t)->tech->runFinalProgram(ptScale, lightScale, gamma != 0);
+        memcpy(hostRGB, img.data(), sizeof(float) * 3 * img.width() * img.height());
+        return 0;
+    )
+}
+void* evplp_host_pt_handle(void* t) { return ((HostPt*)t)->tech->handle(); }
+void evplp_host_pt_destroy(void* t) { delete (HostPt*)t; }
+
 // The whole blocking call of the reference: RtTechnique::render(scene, resolution, json) + outputs.
 int evplp_host_render_json(const char* jsonPath, int device) {
     GUARD(
@@ -138,6 +166,7 @@ int evplp_host_render_json(const char* jsonPath, int device) {
         shared_ptr<RtScene> scene = LoadScene(json, jsonPath);
         if (!scene) throw std::runtime_error("no scene in json");
         Vec2 res; res.x = json["resX"].as_float(); res.y = json["resY"].as_float();
+        if (!json["pt"].is_null()) { RtPt2 t(device); t.render(scene, res, json["pt"]); }
         if (!json["photonfam"].is_null()) { RtComPhoton t(device); t.render(scene, res, json["photonfam"]); }
         if (!json["lvcphotonfam"].is_null()) { RtLvcComPhoton t(device); t.render(scene, res, json["lvcphotonfam"]); }
         return 0;

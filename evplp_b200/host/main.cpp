@@ -6,6 +6,7 @@
 #include <cstring>
 #include <iostream>
 #include "rtcomphoton.h"
+#include "rtpt2.h"
 #include "scenegen.h"
 
 using namespace evplp_host;
@@ -34,7 +35,11 @@ int main(int numArg, const char* args[]) {
         shared_ptr<RtScene> scene = LoadScene(json, jsonFilename);
         if (!scene) { std::cerr << "no \"scene\" in " << jsonFilename << "\n"; return 1; }
         Vec2 res; res.x = json["resX"].as_float(); res.y = json["resY"].as_float();
-        if (!json["pt"].is_null()) std::cerr << "\"pt\" (RtPt2 path tracer) is outside the EVPLP hot path and not built\n";
+        if (!json["pt"].is_null()) {  // main.cpp:105-109
+            RtPt2 rtpt(device);
+            rtpt.render(scene, res, json["pt"]);
+            std::cout << "pt: " << rtpt.numIterations() << " iterations in " << rtpt.elapsedMs() << " ms\n";
+        }
         if (!json["photonfam"].is_null()) {
             RtComPhoton rtcomp(device);
             rtcomp.render(scene, res, json["photonfam"]);

@@ -475,6 +475,17 @@ inline void ExportScene(const GenScene& g, const std::string& dir, int resX = 12
         std::ofstream of(base + "_" + variant + ".json");
         of << TechniqueJson(g, variant, resX, resY, g.name + "_" + variant);
     }
+    for (const char* variant : {"pt", "pt_progressive"}) {  // scene/*/*_pt.json: the path-traced reference images
+        std::string text = TechniqueJson(g, "ours", resX, resY, g.name + "_" + variant);
+        const size_t a = text.find("    \"photonfam\"");
+        std::ostringstream o;
+        o << text.substr(0, a) << "    \"pt\": {\n        \"rngOffset\": 0,\n        \"numMaxIteration\": 64,\n        \"timeLimitMs\": 15000.0,\n"
+          << "        \"frameMode\": \"accumulate\",\n        \"outputFilename\": \"" << g.name << "_" << variant << ".pfm\",\n"
+          << "        \"statFilename\": \"" << g.name << "_" << variant << "_stat.json\",\n        \"useJitter\": true,\n        \"useStat\": true,\n"
+          << "        \"numSamplePerPixel\": 1,\n        \"numMaxBounces\": 3,\n        \"DoProgressive\": false,\n        \"AlphaProgressive\": 0.7\n    }\n}\n";
+        std::ofstream of(base + "_" + variant + ".json");
+        of << o.str();
+    }
 }
 
 }  // namespace evplp_host

@@ -44,6 +44,13 @@ def load_host_library():
     lib.evplp_host_technique_state.argtypes = [_P, C.POINTER(C.c_float)]
     lib.evplp_host_technique_final.argtypes = [_P, C.c_float, C.c_float, C.c_float, C.c_int, _P]
     lib.evplp_host_technique_destroy.argtypes = [_P]
+    lib.evplp_host_pt_create.restype = _P
+    lib.evplp_host_pt_create.argtypes = [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.evplp_host_pt_iterate.argtypes = [_P]
+    lib.evplp_host_pt_final.argtypes = [_P, C.c_float, C.c_float, C.c_int, _P]
+    lib.evplp_host_pt_handle.restype = _P
+    lib.evplp_host_pt_handle.argtypes = [_P]
+    lib.evplp_host_pt_destroy.argtypes = [_P]
     lib.evplp_host_render_json.argtypes = [C.c_char_p, C.c_int]
     lib.evplp_host_progressive_update.argtypes = [C.c_int32, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, _P]
     lib.evplp_host_jitter_stream.argtypes = [C.c_uint32, C.c_uint32, _P]
@@ -184,6 +191,41 @@ class Technique:
     def close(self):
         if self.h:
             self.lib.evplp_host_technique_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PathTracer:
+    """RtPt2 of the C++ host library (the reference's ground-truth technique), stepped one iteration at a time."""
+
+    def __init__(self, host_scene, pt, res_x, res_y, device=0, rank=0, world_size=1):
+        self.lib = load_host_library()
+        self.W, self.H = res_x, res_y
+        self.h = self.lib.evplp_host_pt_create(host_scene.h, json.dumps(pt).encode(), res_x, res_y, device, rank, world_size)
+        if not self.h:
+            _err(self.lib, "evplp_host_pt_create")
+        self._scene = host_scene
+
+    def iterate(self):
+        rc = self.lib.evplp_host_pt_iterate(self.h)
+        if rc < 0:
+            _err(self.lib, "evplp_host_pt_iterate")
+        return rc == 1
+
+    def final(self, pt_scale, light_scale, gamma=False):
+        out = np.empty((self.H, self.W, 3), dtype=np.float32)
+        if self.lib.evplp_host_pt_final(self.h, pt_scale, light_scale, 1 if gamma else 0, capi.ptr(out)) != 0:
+            _err(self.lib, "evplp_host_pt_final")
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.evplp_host_pt_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -184,6 +184,12 @@ int evplp_light_trace(evplp_handle h, uint32_t rngSeed, uint32_t firstPath, uint
  * tile == NULL means the whole image. */
 int evplp_vpl_gather(evplp_handle h, const EvplpTile* tile, int gatherMode);
 
+/* RtPt2, replaces runOptixPtProgram -> splatColor / pathTraceSimple / rtMaterialClosestHit
+ * (rtpt/rtpt2.h:561-570; pathtracing.cu:112-377): one path per pixel from the G-buffer first hit with next-event
+ * estimation + MIS, per-pixel stream curand_init(pixel, params.rngSeed, 0); the result is added to (doAccumulate) or
+ * replaces the VPL accumulation layer (the technique's outputBuffer).  The reference's own ground-truth generator. */
+int evplp_path_trace(evplp_handle h, const EvplpTile* tile, uint32_t maxBounces);
+
 /* replaces runPhotonSplat (rtcomphoton.h:789-837; shaders/photonsplatinstanced.*).
  * firstRecord/numRecords index the record window written by the last evplp_light_trace. */
 int evplp_photon_splat(evplp_handle h, uint64_t firstRecord, uint64_t numRecords, const EvplpTile* tile);

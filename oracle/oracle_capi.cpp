@@ -235,6 +235,27 @@ void orc_vpl_gather(void* h, const EvplpParams* P, int32_t W, int32_t H, const f
     if (counters) { counters[0] += pairs; counters[1] += rays; }
 }
 
+// RtPt2 path tracer (pathtracing.cu): outRGB[W*H*3] = one path per pixel of the tile; counters[0] += rays traced
+void orc_path_trace(void* h, const EvplpParams* P, int32_t W, int32_t H, const float* planes, const int32_t* primIds, uint32_t maxBounces,
+                    const EvplpTile* tile, float* outRGB, uint64_t* counters) {
+    Scene* s = (Scene*)h;
+    const int64_t n = (int64_t)W * H;
+    EvplpTile t = tile ? *tile : EvplpTile{0, 0, W, H};
+    uint64_t rays = 0;
+    memset(outRGB, 0, sizeof(float) * 3 * n);
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : rays)
+    for (int64_t i = 0; i < n; i++) {
+        int x = (int)(i % W), y = (int)(i / W);
+        if (x < t.x0 || x >= t.x1 || y < t.y0 || y >= t.y1) continue;
+        GPixel g; unpack_gpixel(planes, primIds, n, i, g);
+        uint64_t r = 0;
+        F3 c = pt::splatColor(*s, *P, g, (unsigned)i, maxBounces, &r);
+        outRGB[i * 3] = c.x; outRGB[i * 3 + 1] = c.y; outRGB[i * 3 + 2] = c.z;
+        rays += r;
+    }
+    if (counters) counters[0] += rays;
+}
+
 // accum[W*H*3] (int64, Q31.32) += fixed(value)
 void orc_accumulate_fixed(const float* rgb, int64_t count, int64_t* accum) {
     for (int64_t i = 0; i < count; i++) accum[i] += to_fixed(rgb[i]);

@@ -615,6 +615,199 @@ inline F3 splatSplotch(const Scene& s, const EvplpParams& P, const GPixel& g, co
     return result / (float)P.numVplLightPaths;
 }
 
+// ------------------------------- pathtracing.cu (RtPt2) ----------------------------
+// The reference's own ground-truth technique: pathtracing.cu:49-52, 85-95, 112-218, 232-377.
+namespace pt {
+inline float russianProb(const F3& throughput) {  // :49-52 (sic: never below 0.98)
+    return fmaxf(fmaxf(throughput.x, 0.98f), fmaxf(throughput.y, throughput.z));
+}
+inline float MisWeight(const float pdf1, const float pdf2) { return pdf1 / (pdf1 + pdf2); }  // :85-88
+inline float pdfW2A(const F3& n2, const F3& v12) {                                           // :90-94
+    F3 nv12 = normalize(v12);
+    return fmaxf(-dot(n2, nv12), 0.f) / dot(v12, v12);
+}
+inline float GeometryTerm(const F3& n1, const F3& n2, const F3 v12) {  // rtmaterial.cuh:30-38
+    const float cos1Unnorm = fmaxf(dot(n1, v12), 0.f);
+    const float cos2Unnorm = fmaxf(-dot(n2, v12), 0.f);
+    const float d2 = dot(v12, v12);
+    return cos1Unnorm * cos2Unnorm / (d2 * d2);
+}
+inline F3 LambertEval(const F3&, const F3&, const F3&, const F3& lambertReflectance) { return lambertReflectance * M_Inv_PIf; }  // :69-72
+inline F3 PhongEval(const F3& out, const F3& in, const F3& normal, const F3& phongReflectance, const float phongExponent) {  // :104-111
+    F3 reflectVec = reflect(-in, normal);
+    float dotWrWo = fmaxf(dot(out, reflectVec), 0.0f);
+    if (dotWrWo <= 0.000001f || phongReflectance.x <= 0.000001f) { return mk3(0.0f); }
+    return phongReflectance * (phongExponent + 2.0f) * det_powf(dotWrWo, phongExponent) * (M_Inv_PIf) * 0.5f;
+}
+
+struct PerRayData_radiance {
+    bool done;
+    CurandState* rngState;
+    float brdfPdfW;
+    F3 result, position, direction, attenuation;
+};
+
+// rtMaterialClosestHit (:112-218)
+inline void rtMaterialClosestHit(const Scene& s, PerRayData_radiance& prdRadiance, const F3& rayOrigin, const F3& rayDirection,
+                                 const Hit& hit, uint64_t* rays) {
+    const Tri& tri = s.tris[hit.prim];
+    const Material& mat = s.mats[tri.mat];
+    F3 geometryNormal = normalize(hit.n);
+    F2 texcoord;
+    {
+        float w0 = 1.0f - hit.beta - hit.gamma;
+        texcoord.x = tri.t1.x * hit.beta + tri.t2.x * hit.gamma + tri.t0.x * w0;
+        texcoord.y = tri.t1.y * hit.beta + tri.t2.y * hit.gamma + tri.t0.y * w0;
+    }
+    F3 worldGeometryNormal = normalize(geometryNormal);
+    F3 ffNormal = faceforward(worldGeometryNormal, -rayDirection, worldGeometryNormal);
+    F3 nextPosition = rayOrigin + hit.t * rayDirection;
+
+    if (dot(geometryNormal, rayDirection) > 0.f) {
+        prdRadiance.result = mk3(0.0f);
+        prdRadiance.done = true;
+        return;
+    }
+    if (mat.lightIntensity[0] > 0.01f) {
+        float brdfPdfA = (prdRadiance.brdfPdfW * pdfW2A(ffNormal, nextPosition - prdRadiance.position));
+        float lightPdfA = 1.f / s.lightArea;
+        float weight = MisWeight(brdfPdfA, lightPdfA);
+        prdRadiance.result = weight * prdRadiance.attenuation *
+                             PhongEvalF(geometryNormal, normalize(prdRadiance.position - nextPosition), geometryNormal, mat.lightIntensity[3]) *
+                             mk3(mat.lightIntensity[0], mat.lightIntensity[1], mat.lightIntensity[2]);
+        prdRadiance.done = true;
+        return;
+    }
+    if (prdRadiance.done) { return; }
+
+    float lightPdf;
+    F3 lightPosition, lightNormal;
+    F3 lightValue = LightSample(s, &lightPosition, &lightNormal, &lightPdf, prdRadiance.rngState);
+    F3 toLight = lightPosition - nextPosition;
+    F3 toLightNorm = normalize(toLight);
+    (*rays)++;
+    bool shadowHit = trace_any(s, lightPosition, -toLight, (float)0.00001, (float)0.99999);
+
+    float tl[4], tp[4], te[4];
+    tex2D(mat.lambert, texcoord.x, texcoord.y, tl);
+    tex2D(mat.phong, texcoord.x, texcoord.y, tp);
+    tex2D(mat.exponent, texcoord.x, texcoord.y, te);
+    F3 lambertReflectance = mk3(tl[0], tl[1], tl[2]);
+    F3 phongReflectance = mk3(tp[0], tp[1], tp[2]);
+    float phongExponent = te[0];
+
+    float maxLambert = MaxColor(lambertReflectance);
+    float maxPhong = MaxColor(phongReflectance);
+    prdRadiance.done = (maxLambert + maxPhong <= 0.000001f);
+    if (prdRadiance.done) { return; }
+
+    float pSelectLambert = maxLambert / (maxPhong + maxLambert);
+    float chooseMaterial = fminf(curand_uniform(prdRadiance.rngState), 0.999999f);
+    const float lightExp = s.lightIntensity[3];
+    if (chooseMaterial < pSelectLambert) {
+        if (!shadowHit) {
+            float brdfPdf = LambertPdfA(ffNormal, lightNormal, toLight);
+            float weight = MisWeight(lightPdf, brdfPdf);
+            prdRadiance.result = weight * lightValue *
+                                 LambertEval(toLightNorm, normalize(prdRadiance.position - nextPosition), ffNormal, lambertReflectance) *
+                                 GeometryTerm(ffNormal, lightNormal, toLight) * prdRadiance.attenuation / pSelectLambert *
+                                 PhongEvalF(lightNormal, -toLightNorm, lightNormal, lightExp);
+        }
+        prdRadiance.attenuation *= LambertSample(&prdRadiance.direction, &prdRadiance.brdfPdfW,
+                                                 normalize(prdRadiance.position - nextPosition), geometryNormal, lambertReflectance,
+                                                 prdRadiance.rngState) / pSelectLambert;
+    } else {
+        if (!shadowHit) {
+            float brdfPdf = PhongPdfA(ffNormal, lightNormal, toLight, normalize(prdRadiance.position - nextPosition), phongReflectance, phongExponent);
+            float weight = MisWeight(lightPdf, brdfPdf);
+            prdRadiance.result = weight * lightValue *
+                                 PhongEval(toLightNorm, normalize(prdRadiance.position - nextPosition), ffNormal, phongReflectance, phongExponent) *
+                                 GeometryTerm(ffNormal, lightNormal, toLight) * prdRadiance.attenuation / (1.0f - pSelectLambert) *
+                                 PhongEvalF(lightNormal, -toLightNorm, lightNormal, lightExp);
+        }
+        prdRadiance.attenuation *= PhongSample(&prdRadiance.direction, &prdRadiance.brdfPdfW,
+                                               normalize(prdRadiance.position - nextPosition), geometryNormal, phongReflectance,
+                                               phongExponent, prdRadiance.rngState) / (1.0f - pSelectLambert);
+    }
+    float russian = pt::russianProb(prdRadiance.attenuation);
+    prdRadiance.done = (curand_uniform(prdRadiance.rngState) >= russian);
+    if (prdRadiance.done) { return; }
+    prdRadiance.position = nextPosition;
+    prdRadiance.attenuation /= russian;
+}
+
+// pathTraceSimple (:232-321) with numSamples = 1
+inline F3 pathTraceSimple(const Scene& s, const F3& cameraPos, const F3& firstPosition, const F3& firstNormal,
+                          const F3& firstLambertReflectance, const F3& firstPhongReflectance, const float firstPhongExponent,
+                          unsigned maxBounces, CurandState* rngState, uint64_t* rays) {
+    F3 cameraVec = normalize(firstPosition - cameraPos);
+    F3 result = mk3(0.0f);
+    PerRayData_radiance prd;
+    prd.rngState = rngState;
+    F3 position = firstPosition;
+    F3 normal = firstNormal;
+    prd.position = firstPosition;
+    prd.attenuation = mk3(1.0f);
+    prd.brdfPdfW = 0.f;
+    prd.direction = mk3(0.f);
+    const float lightExp = s.lightIntensity[3];
+    {
+        float lightPdf;
+        F3 lightPosition, lightNormal;
+        F3 lightValue = LightSample(s, &lightPosition, &lightNormal, &lightPdf, rngState);
+        F3 toLight = lightPosition - position;
+        F3 toLightNorm = normalize(toLight);
+        (*rays)++;
+        bool shadowHit = trace_any(s, lightPosition, -toLight, 0.0001f, 1.0f - 0.0001f);
+        float maxLambert = MaxColor(firstLambertReflectance);
+        float maxPhong = MaxColor(firstPhongReflectance);
+        float pSelectLambert = maxLambert / (maxPhong + maxLambert);
+        if (maxLambert + maxPhong <= 0.000001f) { return mk3(0.0f); }
+        float chooseMaterial = fminf(curand_uniform(prd.rngState), 0.999999f);
+        if (chooseMaterial < pSelectLambert) {
+            if (!shadowHit) {
+                float brdfPdf = LambertPdfA(normal, lightNormal, toLight);
+                float weight = MisWeight(lightPdf, brdfPdf);
+                result += weight * lightValue * LambertEval(-cameraVec, toLightNorm, normal, firstLambertReflectance) *
+                          GeometryTerm(normal, lightNormal, toLight) / pSelectLambert *
+                          PhongEvalF(lightNormal, -toLightNorm, lightNormal, lightExp);
+            }
+            prd.attenuation *= LambertSample(&prd.direction, &prd.brdfPdfW, -cameraVec, normal, firstLambertReflectance, prd.rngState) / pSelectLambert;
+        } else {
+            if (!shadowHit) {
+                float brdfPdf = PhongPdfA(normal, lightNormal, toLight, -cameraVec, firstPhongReflectance, firstPhongExponent);
+                float weight = MisWeight(lightPdf, brdfPdf);
+                result += weight * lightValue * PhongEval(-cameraVec, toLightNorm, normal, firstPhongReflectance, firstPhongExponent) *
+                          GeometryTerm(normal, lightNormal, toLight) / (1.0f - pSelectLambert) *
+                          PhongEvalF(lightNormal, -toLightNorm, lightNormal, lightExp);
+            }
+            prd.attenuation *= PhongSample(&prd.direction, &prd.brdfPdfW, -cameraVec, normal, firstPhongReflectance, firstPhongExponent,
+                                           prd.rngState) / (1.0f - pSelectLambert);
+        }
+    }
+    for (size_t i = 0; i < maxBounces; i++) {
+        prd.done = (i == maxBounces - 1);
+        prd.result = mk3(0.f);
+        const F3 rayOrigin = prd.position, rayDirection = prd.direction;
+        (*rays)++;
+        Hit hit = trace_closest(s, rayOrigin, rayDirection, (float)0.00001, 1e27f);
+        if (hit.prim < 0) { break; }  // no miss program: the same miss repeats until the last bounce, nothing is added
+        rtMaterialClosestHit(s, prd, rayOrigin, rayDirection, hit, rays);
+        result += prd.result;
+        if (prd.done) { break; }
+    }
+    return result;
+}
+
+// splatColor (:323-354): result of one pixel (the caller accumulates)
+inline F3 splatColor(const Scene& s, const EvplpParams& P, const GPixel& g, unsigned launchId, unsigned maxBounces, uint64_t* rays) {
+    if (g.w == 0.0f) return mk3(0.f);
+    CurandState localState;
+    curand_init(launchId, P.rngSeed, 0, &localState);
+    return pathTraceSimple(s, getv(P.cameraPosition), g.position, g.normal, g.lambert, g.phong, g.exponent, maxBounces, &localState, rays);
+}
+}  // namespace pt
+
 // ------------------------------- photonsplatinstanced.frag --------------------------
 namespace glsl {
 inline F3 LambertEval(const F3& w10, const F3& w12, const F3& normal, const F3& lambertReflectance) {  // .frag:36-44

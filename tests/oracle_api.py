@@ -52,6 +52,7 @@ def load():
     lib.orc_gbuffer.argtypes = [_P, C.POINTER(capi.Params), C.c_int32, C.c_int32, _P, _P]
     lib.orc_vpl_gather.argtypes = [_P, C.POINTER(capi.Params), C.c_int32, C.c_int32, _P, _P, _P, C.c_int32,
                                    C.POINTER(capi.Tile), _P, _P]
+    lib.orc_path_trace.argtypes = [_P, C.POINTER(capi.Params), C.c_int32, C.c_int32, _P, _P, C.c_uint32, C.POINTER(capi.Tile), _P, _P]
     lib.orc_accumulate_fixed.argtypes = [_P, C.c_int64, _P]
     lib.orc_photon_splat.argtypes = [C.POINTER(capi.Params), C.c_int32, C.c_int32, _P, _P, _P, C.c_uint64, C.c_uint64,
                                      C.POINTER(capi.Tile), _P, _P, C.c_int32]
@@ -98,6 +99,14 @@ class OracleScene:
         records = np.ascontiguousarray(records)
         self.lib.orc_vpl_gather(self.h, C.byref(params), W, H, capi.ptr(planes), capi.ptr(prims), capi.ptr(records), mode, t,
                                 capi.ptr(out), capi.ptr(counters))
+        return out, counters
+
+    def path_trace(self, params, W, H, planes, prims, max_bounces, tile=None):
+        out = np.empty((H, W, 3), dtype=np.float32)
+        counters = np.zeros(1, dtype=np.uint64)
+        t = C.byref(capi.Tile(*tile)) if tile is not None else None
+        self.lib.orc_path_trace(self.h, C.byref(params), W, H, capi.ptr(planes), capi.ptr(prims), max_bounces, t, capi.ptr(out),
+                                capi.ptr(counters))
         return out, counters
 
     def accumulate_fixed(self, rgb, accum):

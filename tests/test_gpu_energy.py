@@ -37,3 +37,28 @@ def test_clamp_plus_compensation_conserves_energy():
     # balance-heuristic MIS (the bundled default) combines the two estimators with weights that sum to one as well
     mis_vpl, mis_photon = _render(hs, misMode="balance")
     assert abs((mis_vpl.sum() + mis_photon.sum()) - e_ref) < 0.05 * e_ref
+
+
+def test_path_tracer_agrees_with_vpl_and_energy_compensated_renders():
+    """Independent ground truth: RtPt2 (NEE + MIS path tracer, numMaxBounces 3) and the VPL / EVPLP renders cover the same
+    light transport (direct + two indirect bounces) and must converge to the same image energy."""
+    hs = HA.HostScene.generate("livingroom", 4, 2, W / H)
+    pt = HA.PathTracer(hs, {"rngOffset": 0, "numMaxIteration": -1, "timeLimitMs": -1.0, "frameMode": "accumulate", "outputFilename": "pt.pfm",
+                            "statFilename": "s.json", "useJitter": True, "useStat": False, "numSamplePerPixel": 1, "numMaxBounces": 3}, W, H)
+    n = 256
+    for _ in range(n):
+        pt.iterate()
+    img_pt = pt.final(1.0 / n, 0.0).astype(np.float64)
+    pt.close()
+    ref_vpl, _ = _render(hs, misMode="one", radiusPercentage=0.0)
+    ours_vpl, ours_photon = _render(hs, misMode="geometryClamp", clampingCoeff=0.02)
+    e_pt, e_vpl, e_ours = img_pt.sum(), ref_vpl.sum(), (ours_vpl + ours_photon).sum()
+    assert e_pt > 0
+    assert abs(e_vpl - e_pt) < 0.05 * e_pt
+    assert abs(e_ours - e_pt) < 0.06 * e_pt
+    # and pixel-wise on a 4x4-blocked image (averages out the Monte-Carlo noise): relative RMSE small
+    def blocks(a):
+        return a[: H // 6 * 6, : W // 8 * 8].reshape(H // 6, 6, W // 8, 8, 3).mean(axis=(1, 3))
+    a, b = blocks(img_pt), blocks(ours_vpl + ours_photon)
+    rel = np.sqrt(((a - b) ** 2).mean()) / a.mean()
+    assert rel < 0.25

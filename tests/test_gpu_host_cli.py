@@ -109,3 +109,25 @@ def test_lvc_technique_runs_through_the_host_class(tmp_path):
     exp = (t.final(0.0, 0.0, 1.0) + t.final(1.0, 0.0, 0.0) * half) + t.final(0.0, 1.0, 0.0) * half
     t.close()
     assert comb.mean() > 1e-4 and np.array_equal(comb, exp)
+
+
+def test_cli_path_tracer_json(tmp_path):
+    """scene/*/*_pt.json -> RtPt2::render (main.cpp:105-109): output = light + pt / N, flipped, PFM."""
+    d = str(tmp_path)
+    HA.export_scene("livingroom", d, seed=3, detail=2, res_x=160, res_y=90)
+    jpath = os.path.join(d, "livingroom_pt.json")
+    j = json.load(open(jpath))
+    j["pt"].update(numMaxIteration=5, timeLimitMs=600000.0)
+    json.dump(j, open(jpath, "w"))
+    r = subprocess.run([EXE, jpath], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "pt: 5 iterations" in r.stdout
+    img = _read_pfm_rows(os.path.join(d, j["pt"]["outputFilename"]))
+    hs = HA.HostScene.load(jpath)
+    t = HA.PathTracer(hs, j["pt"], 160, 90)
+    for _ in range(5):
+        t.iterate()
+    exp = t.final(0.0, 1.0) + t.final(1.0, 0.0) * np.float32(1.0 / 5)
+    t.close()
+    assert img.mean() > 1e-4 and np.array_equal(img, exp)
+    assert json.load(open(os.path.join(d, j["pt"]["statFilename"])))["numIterations"] == 5

@@ -328,3 +328,25 @@ def test_directional_light_and_diffuse_scene():
         assert got.tobytes() == exp.tobytes()
     finally:
         r.dev.close()
+
+
+@pytest.mark.parametrize("bounces", [1, 3, 6])
+def test_path_tracer_bit_exact(rig, bounces):
+    """RtPt2 (pathtracing.cu): one path per pixel with NEE + MIS; per-pixel XORWOW streams; bit-exact incl. ray counts."""
+    P = rig.params(accumulate=True, rng_seed=11)
+    rig.dev.set_params(P)
+    rig.dev.gbuffer()
+    planes, prims = rig.orc.gbuffer(P, W, H)
+    exp, cnt = rig.orc.path_trace(P, W, H, planes, prims, bounces)
+    eacc = np.zeros((H, W, 3), dtype=np.int64)
+    rig.orc.accumulate_fixed(exp, eacc)
+    rig.orc.accumulate_fixed(exp, eacc)
+    assert eacc.sum() > 0
+    rig.dev.clear_accum()
+    rig.dev.reset_stats()
+    rig.dev.path_trace(bounces)
+    rig.dev.path_trace(bounces, tile=(0, 0, 50, H))   # accumulates (doAccumulate = 1), ragged tiles
+    rig.dev.path_trace(bounces, tile=(50, 0, W, H))
+    vpl, _, _ = rig.dev.download_accum()
+    assert np.array_equal(vpl, eacc)
+    assert rig.dev.stats().closestRays == 2 * int(cnt[0])
