@@ -192,4 +192,25 @@ float evplp_host_pfm_relmse(const char* a, const char* b) {
     catch (const std::exception& e) { g_hostErr = e.what(); return -1.f; }
 }
 
+
+// texture decoding taps: a JPEG byte stream -> top-down RGB8 (what stbi_load(path, .., 3) returns without the
+// flip), and a texture file -> the RGBA32F texels RtTexture hands to evplp_upload_scene
+int evplp_host_jpeg_info(const uint8_t* data, uint64_t n, int32_t* width, int32_t* height, int32_t* fileChannels) {
+    GUARD(jpeg::Image img; jpeg::Decode(data, (size_t)n, &img); *width = img.width; *height = img.height;
+          *fileChannels = img.fileChannels; return 0;)
+}
+int evplp_host_jpeg_decode(const uint8_t* data, uint64_t n, uint8_t* rgbOut, uint64_t rgbCapacity) {
+    GUARD(jpeg::Image img; jpeg::Decode(data, (size_t)n, &img);
+          if (img.rgb.size() > rgbCapacity) throw std::runtime_error("evplp_host_jpeg_decode: output buffer too small");
+          memcpy(rgbOut, img.rgb.data(), img.rgb.size()); return 0;)
+}
+int evplp_host_texture_load(const char* path, float gamma, int32_t* width, int32_t* height, float* rgbaOut, uint64_t capacityFloats) {
+    GUARD(RtTexture t(std::string(path), gamma); *width = t.mWidth; *height = t.mHeight;
+          if (rgbaOut) {
+              if (t.mData.size() > capacityFloats) throw std::runtime_error("evplp_host_texture_load: output buffer too small");
+              memcpy(rgbaOut, t.mData.data(), t.mData.size() * sizeof(float));
+          }
+          return 0;)
+}
+
 }  // extern "C"

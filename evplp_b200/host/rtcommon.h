@@ -10,10 +10,11 @@
 // identical (position, texcoord) vertices joined, material 0 = Assimp's "DefaultMaterial",
 // Kd / Ks / Ns with the reference's "shininess / 4" correction of Assimp's 4x scaling
 // (i.e. the exponent is the MTL Ns), map_Kd / map_Ks / map_Ns textures flipped vertically,
-// value/255 with gamma 1, alpha 0.  Texture files must be binary PPM/PGM (stb_image reads
-// those too); JPG/PNG decoding is not built.
+// value/255 with gamma 1, alpha 0.  Texture files: JPEG (jpegdecode.h, bit-exact with the
+// reference's stb_image v2.16) or binary PPM/PGM (stb_image reads those too).
 #pragma once
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -26,6 +27,7 @@
 #include <vector>
 #include "../../include/evplp.h"
 #include "json.h"
+#include "jpegdecode.h"
 
 namespace evplp_host {
 
@@ -72,34 +74,58 @@ struct RtTexture {
     RtTexture(const std::string& filepath, float gamma) {
         std::ifstream f(filepath, std::ios::binary);
         if (!f.is_open()) throw std::runtime_error("RtTexture: cannot open " + filepath);
-        std::string magic;
-        f >> magic;
-        if (magic != "P6" && magic != "P5")
-            throw std::runtime_error("RtTexture: " + filepath + " is not a binary PPM/PGM (JPG/PNG decoding is not built; convert the texture)");
-        auto next_int = [&]() {
-            std::string tok;
-            while (f >> tok) {
-                if (tok[0] == '#') { std::string rest; std::getline(f, rest); continue; }
-                return atoi(tok.c_str());
+        std::vector<unsigned char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        std::vector<unsigned char> rgb;  // top-down, 3 channels (stbi_load(.., 3))
+        if (jpeg::IsJpeg(bytes.data(), bytes.size())) {
+            jpeg::Image img;
+            try {
+                jpeg::Decode(bytes.data(), bytes.size(), &img);
+            } catch (const std::exception& e) {
+                throw std::runtime_error("RtTexture: " + filepath + ": " + e.what());
             }
-            throw std::runtime_error("RtTexture: truncated header in " + filepath);
-        };
-        mWidth = next_int(); mHeight = next_int();
-        int maxv = next_int();
-        f.get();
-        if (maxv != 255 || mWidth <= 0 || mHeight <= 0) throw std::runtime_error("RtTexture: unsupported PPM in " + filepath);
-        const int ch = magic == "P6" ? 3 : 1;
-        std::vector<unsigned char> raw((size_t)mWidth * mHeight * ch);
-        f.read((char*)raw.data(), (std::streamsize)raw.size());
-        if ((size_t)f.gcount() != raw.size()) throw std::runtime_error("RtTexture: truncated data in " + filepath);
+            mWidth = img.width; mHeight = img.height;
+            rgb.swap(img.rgb);
+        } else {
+            decodePnm(bytes, filepath, &rgb);
+        }
         mData.resize((size_t)mWidth * mHeight * 4);
         for (int y = 0; y < mHeight; y++)
             for (int x = 0; x < mWidth; x++) {
-                const unsigned char* src = &raw[((size_t)(mHeight - 1 - y) * mWidth + x) * ch];  // flip vertically
+                const unsigned char* src = &rgb[((size_t)(mHeight - 1 - y) * mWidth + x) * 3];  // flip vertically
                 float* dst = &mData[((size_t)y * mWidth + x) * 4];
-                for (int c = 0; c < 3; c++) dst[c] = std::pow((float)src[ch == 3 ? c : 0] / 255.0f, gamma);
+                for (int c = 0; c < 3; c++) dst[c] = std::pow((float)src[c] / 255.0f, gamma);
                 dst[3] = 0.f;
             }
+    }
+
+private:
+    // binary PPM / PGM (what the scene generator writes)
+    void decodePnm(const std::vector<unsigned char>& bytes, const std::string& filepath, std::vector<unsigned char>* rgb) {
+        size_t pos = 0;
+        auto next_token = [&]() {
+            for (;;) {
+                while (pos < bytes.size() && isspace(bytes[pos])) pos++;
+                if (pos < bytes.size() && bytes[pos] == '#') { while (pos < bytes.size() && bytes[pos] != '\n') pos++; continue; }
+                break;
+            }
+            std::string tok;
+            while (pos < bytes.size() && !isspace(bytes[pos])) tok.push_back((char)bytes[pos++]);
+            if (tok.empty()) throw std::runtime_error("RtTexture: truncated header in " + filepath);
+            return tok;
+        };
+        const std::string magic = bytes.size() >= 2 ? next_token() : std::string();
+        if (magic != "P6" && magic != "P5")
+            throw std::runtime_error("RtTexture: " + filepath + " is neither JPEG nor binary PPM/PGM (the reference's scenes use JPEG only)");
+        mWidth = atoi(next_token().c_str()); mHeight = atoi(next_token().c_str());
+        const int maxv = atoi(next_token().c_str());
+        pos++;  // the single whitespace after maxval
+        if (maxv != 255 || mWidth <= 0 || mHeight <= 0) throw std::runtime_error("RtTexture: unsupported PPM in " + filepath);
+        const int ch = magic == "P6" ? 3 : 1;
+        const size_t n = (size_t)mWidth * mHeight;
+        if (bytes.size() - pos < n * ch) throw std::runtime_error("RtTexture: truncated data in " + filepath);
+        rgb->resize(n * 3);
+        for (size_t i = 0; i < n; i++)
+            for (int c = 0; c < 3; c++) (*rgb)[i * 3 + c] = bytes[pos + i * ch + (ch == 3 ? c : 0)];
     }
 };
 

@@ -57,6 +57,9 @@ def load_host_library():
     lib.evplp_host_save_pfm.argtypes = [C.c_char_p, _P, C.c_int, C.c_int]
     lib.evplp_host_pfm_relmse.restype = C.c_float
     lib.evplp_host_pfm_relmse.argtypes = [C.c_char_p, C.c_char_p]
+    lib.evplp_host_jpeg_info.argtypes = [_P, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.evplp_host_jpeg_decode.argtypes = [_P, C.c_uint64, _P, C.c_uint64]
+    lib.evplp_host_texture_load.argtypes = [C.c_char_p, C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.c_uint64]
     _lib = lib
     return lib
 
@@ -239,6 +242,32 @@ def export_scene(name, out_dir, seed=1, detail=8, res_x=1280, res_y=720):
     lib = load_host_library()
     if lib.evplp_host_export_scene(name.encode(), out_dir.encode(), seed, detail, res_x, res_y) != 0:
         _err(lib, "evplp_host_export_scene")
+
+
+def decode_jpeg(data):
+    """JPEG bytes -> (uint8 [H, W, 3] top-down, file channel count): what stbi_load(path, .., 3) gives the reference
+    (rtcommon.h:144) before its vertical flip."""
+    lib = load_host_library()
+    buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+    w, h, ch = C.c_int32(), C.c_int32(), C.c_int32()
+    if lib.evplp_host_jpeg_info(buf, len(data), C.byref(w), C.byref(h), C.byref(ch)) != 0:
+        _err(lib, "evplp_host_jpeg_info")
+    out = np.empty((h.value, w.value, 3), dtype=np.uint8)
+    if lib.evplp_host_jpeg_decode(buf, len(data), out.ctypes.data_as(_P), out.size) != 0:
+        _err(lib, "evplp_host_jpeg_decode")
+    return out, ch.value
+
+
+def load_texture(path, gamma=1.0):
+    """RtTexture(filepath, gamma) (rtcommon.h:139-194): float32 [H, W, 4], row 0 = bottom, alpha 0."""
+    lib = load_host_library()
+    w, h = C.c_int32(), C.c_int32()
+    if lib.evplp_host_texture_load(path.encode(), gamma, C.byref(w), C.byref(h), None, 0) != 0:
+        _err(lib, "evplp_host_texture_load")
+    out = np.empty((h.value, w.value, 4), dtype=np.float32)
+    if lib.evplp_host_texture_load(path.encode(), gamma, C.byref(w), C.byref(h), out.ctypes.data_as(_P), out.size) != 0:
+        _err(lib, "evplp_host_texture_load")
+    return out
 
 
 def render_json(json_path, device=0):
