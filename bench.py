@@ -171,7 +171,7 @@ def run_reference(args):
         "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -341,13 +341,31 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             pps, csec, cores, desc = cpu_sample(1, 0)
             line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc}
-        print(json.dumps(line))
+        emit(line)
     tech.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  The C++ host classes keep the reference's console messages
+    ("Total area computation: ...", rtcomphoton.h:207), so fd 1 is pointed at stderr for everything else."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)

@@ -474,7 +474,7 @@ __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 
         const uint32_t spNew = sp + 4u * (uint32_t)__popc(mi), cpNew = cp + 4u * (uint32_t)__popc(ml);
         if (spNew > spEnd || cpNew > cpEnd) { fallback = true; break; }
         if (hit && !leaf) st_shared_u32(sp + 4u * (uint32_t)__popc(mi & lt), word);
-        if (hit && leaf) st_shared_u32(cp + 4u * (uint32_t)__popc(ml & lt), word);
+        if (hit && leaf) st_shared_u32(cp + 4u * (uint32_t)__popc(ml & lt), (cur << 5) | lane);  // slot of the leaf: its word AND its box
         sp = spNew; cp = cpNew;
         __syncwarp();
         if (sp == stackBase) break;
@@ -489,16 +489,28 @@ __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 
     const uint32_t cn = (cp - candBase) >> 2;
     counters[2] += cn;
     bool occ = false;
-    for (uint32_t k = 0; k < cn; k++) {
-        const uint32_t w = ld_shared_u32(candBase + 4u * k);
-        const uint32_t first = bvh_leaf_first(w), count = bvh_leaf_count(w);
-        const float4* tp = sc.triLeaf + 4 * (size_t)first;
-        for (uint32_t j = 0; j < count; j++, tp += 4) {
-            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
-            float t, be, ga;
-            occ |= tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga);
+    if (cn) {
+        // A leaf is a candidate when its box meets the SHAFT; most of them meet no individual ray of it.  One slab test
+        // per ray against the (padded) leaf box -- the same conservative test the per-ray traversals descend by --
+        // skips the exact triangle tests of such leaves for the whole warp.
+        const RaySlabM rs = make_slab_masked(org, dir);
+        for (uint32_t k = 0; k < cn; k++) {
+            const uint32_t slot = ld_shared_u32(candBase + 4u * k);
+            const float* nb = base + (slot >> 5) * NODE_F + (slot & 31u);
+            const bool inBox = active && !occ &&
+                               slab_masked(rs, __ldg(nb), __ldg(nb + SHAFT_WIDTH), __ldg(nb + 2 * SHAFT_WIDTH), __ldg(nb + 3 * SHAFT_WIDTH),
+                                           __ldg(nb + 4 * SHAFT_WIDTH), __ldg(nb + 5 * SHAFT_WIDTH), tmin, tmax);
+            if (!__any_sync(full, inBox)) continue;
+            const uint32_t w = __float_as_uint(__ldg(nb + 6 * SHAFT_WIDTH));
+            const uint32_t first = bvh_leaf_first(w), count = bvh_leaf_count(w);
+            const float4* tp = sc.triLeaf + 4 * (size_t)first;
+            for (uint32_t j = 0; j < count; j++, tp += 4) {
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2), d = __ldg(tp + 3);
+                float t, be, ga;
+                occ |= tri_test(org, dir, tmin, tmax, ld3(a), ld3(b), ld3(c), ld3(d), &t, &be, &ga);
+            }
+            if (!__any_sync(full, active && !occ)) break;
         }
-        if (!__any_sync(full, active && !occ)) break;
     }
     __syncwarp();
     return active && occ;

@@ -199,22 +199,51 @@ struct Surface {
     float exponent;
 };
 
+// Terms of the shading tail that depend on the VPL alone.  The gather kernel evaluates them once per VPL when it
+// stages a batch (the same expressions on the same inputs give the same bits wherever they are evaluated).
+struct VplPre {
+    V3 refl;    // reflect(-fluxDir, normal)               (PhongEval, rtmaterial.cuh:113-119)
+    V3 reflN;   // normalize(refl)                         (PhongPdfA, rtmaterial.cuh:88-103)
+    V3 kdPi;    // kInvPi * kd
+};
+EVPLP_HD VplPre vpl_precompute(const Vertex& vp) {
+    VplPre p;
+    p.refl = reflect(-vp.fluxDir, vp.normal);
+    p.reflN = normalize(p.refl);
+    p.kdPi = kInvPi * vp.kd;
+    return p;
+}
+// phong_eval_f / phong_pdf_a with the reflected direction supplied
+EVPLP_HD float phong_eval_f_refl(V3 out, V3 reflectVec, float phongExponent) {
+    float dotWrWo = det_max(dot(out, reflectVec), 0.0f);
+    if (dotWrWo <= 0.000001f) return 0.0f;
+    return (phongExponent + 2.0f) * det_powf(dotWrWo, phongExponent) * (kInvPi) * 0.5f;
+}
+EVPLP_HD float phong_pdf_a_refl(V3 n2, V3 v12, V3 reflectVecN, V3 phongReflectance, float phongExponent) {
+    V3 wi12 = normalize(v12);
+    float cosReflect = det_max(dot(wi12, reflectVecN), 0.f);
+    if (cosReflect <= 0.000001f || phongReflectance.x <= 0.000001f) return 0.0f;
+    float pdfW = (phongExponent + 1.0f) * 0.5f * kInvPi * det_powf(cosReflect, phongExponent);
+    float cos2 = det_max(-dot(n2, wi12), 0.0f);
+    float dist2 = dot(v12, v12);
+    return det_div(pdfW * cos2, dist2);
+}
+
 // Shading tail of vplSplat (lighttracing.cu:296-345) after the cosine test and the shadow
 // ray; c1c2 = unnormCos1 * unnormCos2, v12 = vpl.pos - x.
-EVPLP_HD V3 vpl_shade(const Surface& sf, V3 wi10, const Vertex& vp, V3 v12, float c1c2, unsigned misMode,
-                      float pdfMc, float clampingValue) {
+EVPLP_HD V3 vpl_shade_pre(const Surface& sf, V3 wi10, const Vertex& vp, const VplPre& pre, V3 v12, float c1c2, unsigned misMode,
+                          float pdfMc, float clampingValue) {
     float dist2 = dot(v12, v12);
     float dist = det_sqrtf(dist2);
     V3 wi12 = v12 / dist;
-    V3 incomingDir = vp.fluxDir;
-    V3 brdf2 = kInvPi * vp.kd + phong_eval_f(-wi12, incomingDir, vp.normal, vp.exponent) * vp.ks;
+    V3 brdf2 = pre.kdPi + phong_eval_f_refl(-wi12, pre.refl, vp.exponent) * vp.ks;
     V3 brdf1 = kInvPi * sf.kd + phong_eval_f(wi10, wi12, sf.normal, sf.exponent) * sf.ks;
     float g21 = det_div(c1c2, dist2 * dist2);
     if (misMode == 0) {
         return vp.flux * brdf1 * brdf2 * g21;
     } else if (misMode <= 3) {
         float pdfDe = lambert_pdf_a(vp.normal, sf.normal, -v12) * vp.pSel;
-        pdfDe += phong_pdf_a(vp.normal, sf.normal, -v12, incomingDir, vp.ks, vp.exponent) * (1.0f - vp.pSel);
+        pdfDe += phong_pdf_a_refl(sf.normal, -v12, pre.reflN, vp.ks, vp.exponent) * (1.0f - vp.pSel);
         float weight = misMode == 1 ? balance_heuristic(pdfMc, pdfDe)
                      : misMode == 2 ? max_heuristic(pdfMc, pdfDe) : power_heuristic2(pdfMc, pdfDe);
         return weight * vp.flux * brdf1 * brdf2 * g21;
@@ -224,6 +253,10 @@ EVPLP_HD V3 vpl_shade(const Surface& sf, V3 wi10, const Vertex& vp, V3 v12, floa
         V3 gb = g21 * brdf1 * brdf2;
         return vp.flux * vmin(gb, v3s(clampingValue));
     }
+}
+EVPLP_HD V3 vpl_shade(const Surface& sf, V3 wi10, const Vertex& vp, V3 v12, float c1c2, unsigned misMode,
+                      float pdfMc, float clampingValue) {
+    return vpl_shade_pre(sf, wi10, vp, vpl_precompute(vp), v12, c1c2, misMode, pdfMc, clampingValue);
 }
 
 // ------------------------------------------------------------------ GLSL variants -------

@@ -246,7 +246,9 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
                   DevStats* stats) {
     // Every warp stages its own VPL batches (no block-wide barrier: warps whose pixels are
     // culled by the cosine test run ahead instead of waiting for the slowest warp of the block).
-    __shared__ float4 batchAll[GATHER_WARPS][GATHER_BATCH * 6];
+    // per VPL: the 6 float4 of its record + 3 float4 of shading terms that depend on the VPL alone (VplPre)
+    constexpr int VS = 9;
+    __shared__ float4 batchAll[GATHER_WARPS][GATHER_BATCH * VS];
     __shared__ uint32_t stacks[GATHER_WARPS][BVH_STACK];
     __shared__ uint32_t cands[SHAFT ? GATHER_WARPS : 1][SHAFT_CAND];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -285,11 +287,18 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
         __syncwarp();
         for (uint32_t k = lane; k < nb * 6; k += 32) {
             const uint32_t r = vplList[base + k / 6];
-            batch[k] = __ldg(reinterpret_cast<const float4*>(records + r) + k % 6);
+            batch[(k / 6) * VS + k % 6] = __ldg(reinterpret_cast<const float4*>(records + r) + k % 6);
+        }
+        __syncwarp();
+        if (lane < nb) {
+            const VplPre pre = vpl_precompute(load_vertex(&batch[lane * VS]));
+            batch[lane * VS + 6] = make_float4(pre.refl.x, pre.refl.y, pre.refl.z, 0.f);
+            batch[lane * VS + 7] = make_float4(pre.reflN.x, pre.reflN.y, pre.reflN.z, 0.f);
+            batch[lane * VS + 8] = make_float4(pre.kdPi.x, pre.kdPi.y, pre.kdPi.z, 0.f);
         }
         __syncwarp();
         for (uint32_t j = 0; j < nb; j++) {
-            const float4 a = batch[j * 6], b = batch[j * 6 + 1];
+            const float4 a = batch[j * VS], b = batch[j * VS + 1];
             const V3 vpos = v3(a.x, a.y, a.z), vn = v3(b.x, b.y, b.z);
             const V3 v12 = vpos - sf.pos;
             const float c1 = det_max(dot(sf.normal, v12), 0.0f);
@@ -307,8 +316,11 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
                 occluded = trace_any_warp(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
             }
             if (active && !occluded) {
-                const Vertex vp = load_vertex(&batch[j * 6]);
-                result += vpl_shade(sf, wi01, vp, v12, c1c2, gp.misMode, gp.pdfMc, gp.clampingValue);
+                const Vertex vp = load_vertex(&batch[j * VS]);
+                const float4 p0 = batch[j * VS + 6], p1 = batch[j * VS + 7], p2 = batch[j * VS + 8];
+                VplPre pre;
+                pre.refl = v3(p0.x, p0.y, p0.z); pre.reflN = v3(p1.x, p1.y, p1.z); pre.kdPi = v3(p2.x, p2.y, p2.z);
+                result += vpl_shade_pre(sf, wi01, vp, pre, v12, c1c2, gp.misMode, gp.pdfMc, gp.clampingValue);
             }
         }
     }

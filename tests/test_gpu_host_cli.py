@@ -131,3 +131,40 @@ def test_cli_path_tracer_json(tmp_path):
     t.close()
     assert img.mean() > 1e-4 and np.array_equal(img, exp)
     assert json.load(open(os.path.join(d, j["pt"]["statFilename"])))["numIterations"] == 5
+
+
+def test_jpeg_textured_scene_renders_like_its_decoded_twin(tmp_path):
+    """A real-asset style scene (MTL map_Kd -> JPEG, as the reference's livingroom ships) loaded by the C++ host and
+    rendered on the GPU equals, bit for bit, the same scene with the texture replaced by a PPM holding the pixels the
+    reference's decoder (stb_image, tests/golden/jpeg/expected.npz) produces for that file."""
+    import shutil
+    gold = os.path.join(ROOT, "tests", "golden", "jpeg")
+    exp = np.load(os.path.join(gold, "expected.npz"))
+    images = []
+    for kind in ("jpeg", "ppm"):
+        d = os.path.join(str(tmp_path), kind)
+        os.makedirs(d)
+        HA.export_scene("livingroom", d, seed=3, detail=2, res_x=320, res_y=180)
+        mtl = [f for f in os.listdir(d) if f.endswith(".mtl") and "light" not in f][0]
+        text = open(os.path.join(d, mtl)).read()
+        assert "map_Kd livingroom_wood.ppm" in text
+        if kind == "jpeg":
+            shutil.copy(os.path.join(gold, "prog_420_q95.jpg"), os.path.join(d, "wood.jpg"))
+            text = text.replace("map_Kd livingroom_wood.ppm", "map_Kd wood.jpg")
+        else:
+            px = exp["prog_420_q95"]
+            with open(os.path.join(d, "wood.ppm"), "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (px.shape[1], px.shape[0]) + px.tobytes())
+            text = text.replace("map_Kd livingroom_wood.ppm", "map_Kd wood.ppm")
+        open(os.path.join(d, mtl), "w").write(text)
+        jpath = os.path.join(d, "livingroom_ours.json")
+        fam = json.load(open(jpath))["photonfam"]
+        fam.update(numMaxIteration=2, numLightPaths=20000, numVplLightPaths=64, timeLimitMs=600000.0)
+        hs = HA.HostScene.load(jpath)
+        t = HA.Technique(hs, fam, 320, 180)
+        for _ in range(2):
+            t.iterate()
+        images.append(t.final(1.0, 1.0, 1.0))
+        t.close()
+    assert images[0].mean() > 1e-3
+    assert np.array_equal(images[0], images[1])
