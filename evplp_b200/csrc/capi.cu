@@ -17,7 +17,7 @@ int g_splatGroup = 0;
 int g_bvhLeafMax = BVH_LEAF_MAX;
 int g_shaftLeafMax = 2;
 int g_gatherMode = 1;   // 1 = shaft traversal of the 32-wide hierarchy (default), 0 = per-ray packet traversal
-int g_shaftCandMax = 24;
+int g_shaftCandMax = 96;
 int g_splatMode = 0;
 int g_splatMaxEntries = 256 * 1024 * 1024;
 }

@@ -374,7 +374,7 @@ __device__ __forceinline__ float opaque(float x) { asm volatile("" : "+f"(x)); r
 // COLLECTS candidate leaves; every lane then runs the exact triangle test of its own ray against the
 // candidates' triangles, so the result per ray is the same "exists a triangle that the branchless test
 // accepts" as everywhere else -- the shaft is just another conservative cull.
-constexpr int SHAFT_CAND = 32;  // capacity of the candidate-leaf list; the launch-time limit (shaft_max_candidates) is <= this
+constexpr int SHAFT_CAND = 128;  // capacity of the candidate-leaf list; the launch-time limit (shaft_max_candidates) is <= this
 
 struct Shaft {
     float ilx, ily, ilz, ihx, ihy, ihz;  // 1 / (tileLo - vpl), 1 / (tileHi - vpl) per axis
