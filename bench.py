@@ -304,6 +304,15 @@ def run_gpu(args):
         my_pairs, my_photons = float(st.gatherPairs), float(st.splatPhotons)
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # TFLOP/s
         ach = my_pairs * FLOP_PER_PAIR / max(gather_s, 1e-9) / 1e12
+        # DRAM traffic of one gather launch of the HEADLINE workload from the committed ncu capture (a profiling override
+        # runs a different launch: null)
+        traffic, traffic_src = None, ""
+        tpath = os.path.join(ROOT, "profiles", "r1_gather_traffic_headline_v9.json")
+        overridden = WORKLOAD.startswith("NON-HEADLINE") or bool(args.opt)
+        if not overridden and os.path.exists(tpath):
+            traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
+            traffic_src = ("; traffic = dram__bytes_read + dram__bytes_write of one launch of this workload "
+                           "(profiles/r1_gather_traffic_headline_v9.json): BVH nodes and triangles missing the L2 over 6 s, 1.3 GB/s")
         nrec = PHOTONFAM["numLightPaths"] * 4
         splat_bytes = (96.0 * nrec + 64.0 * RES_X * RES_Y + 48.0 * RES_X * RES_Y) * args.steps
         line = {
@@ -321,11 +330,11 @@ def run_gpu(args):
             "stage_ms_per_step_rank0": {"gbuffer": stage_ms[0] / args.steps, "light_trace": stage_ms[1] / args.steps,
                                         "vpl_gather": stage_ms[2] / args.steps, "photon_splat": stage_ms[3] / args.steps},
             "roofline": {"kernel": "gather_vpl_kernel<4, true> (shaft gather)", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp32_peak, "traffic": None,
+                         "frac": ach / fp32_peak, "traffic": traffic,
                          "note": f"{FLOP_PER_PAIR:.0f} algorithmic FP32 flop per pair (SURVEY 8d) x pairs / gather kernel time; peak = "
                                  f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz ({how} clock); the kernel is shadow-ray traversal bound, "
-                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v7_shaft_ncu_full_summary.txt: 64 % of peak "
-                                 "instruction issue, ALU pipe 47 %, FMA pipe 24 %, DRAM 0.02 %)"},
+                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v9_ncu_full_summary.txt: 65 % of peak "
+                                 "instruction issue, ALU pipe 41 %, FMA pipe 25 %, DRAM 0.03 %)" + traffic_src},
             "roofline_splat": {"kernel": "splat_prepare + splat_fill + splat_tile_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": None,
                                "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}"},

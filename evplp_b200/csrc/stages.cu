@@ -237,13 +237,18 @@ struct GatherParams {
     int shaftMode;               // 1 = shaft traversal (gather_mode option)
     int shaftCandMax;            // shaft gather: candidate leaves beyond which a (warp, VPL) step falls back to the packet traversal
     int bandStride, bandOffset;  // this launch owns the 16-row bands b = bandOffset (mod bandStride) of the tile (multi-GPU interleave)
+    // VPL gather: the launch's (16x16-pixel block, VPL chunk) grid.  With persistent != 0 the kernel is launched with one
+    // resident wave of blocks and every WARP draws the next 8x4-pixel tile of that grid from a global counter, so warps
+    // whose tile is cheap (culled by the cosine test, sky) go on to new work instead of idling until their block ends.
+    unsigned vgx, vgy, vgz;
+    int persistent;
 };
 
 template <int MINB, bool SHAFT>
 __global__ void __launch_bounds__(GATHER_WARPS * 32, MINB)
 gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf, const EvplpRecord* __restrict__ records,
                   const uint32_t* __restrict__ vplList, const uint32_t* __restrict__ vplCount, long long* __restrict__ acc,
-                  DevStats* stats) {
+                  DevStats* stats, uint32_t* __restrict__ tileCounter) {
     // Every warp stages its own VPL batches (no block-wide barrier: warps whose pixels are
     // culled by the cosine test run ahead instead of waiting for the slowest warp of the block).
     // per VPL: the 6 float4 of its record + 3 float4 of shading terms that depend on the VPL alone (VplPre)
@@ -255,8 +260,24 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     float4* batch = batchAll[warp];
     const uint32_t stackBase = opaque((uint32_t)__cvta_generic_to_shared(stacks[warp]));
     const uint32_t candBase = opaque((uint32_t)__cvta_generic_to_shared(cands[SHAFT ? warp : 0]));
-    const int x = gp.x0 + blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = gp.y0 + (blockIdx.y * gp.bandStride + gp.bandOffset) * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t vTotal = gp.vgx * gp.vgy * gp.vgz * GATHER_WARPS;
+    unsigned rays = 0;
+    unsigned shaftCnt[3] = {0u, 0u, 0u}, shaftSteps = 0u;
+    int ovf = 0;
+    for (;;) {
+    // virtual warp v = ((bz * vgy + by) * vgx + bx) * GATHER_WARPS + vw of the block grid
+    uint32_t v;
+    if (gp.persistent) {
+        if (lane == 0) v = atomicAdd(tileCounter, 1u);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if (v >= vTotal) break;
+    } else {
+        v = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * GATHER_WARPS + warp;
+    }
+    const uint32_t vw = v % GATHER_WARPS, vb = v / GATHER_WARPS;
+    const uint32_t bx = vb % gp.vgx, by = (vb / gp.vgx) % gp.vgy, bz = vb / (gp.vgx * gp.vgy);
+    const int x = gp.x0 + bx * 16 + (vw & 1) * 8 + (lane & 7);
+    const int y = gp.y0 + (by * gp.bandStride + gp.bandOffset) * 16 + (vw >> 1) * 4 + (lane >> 3);
     const bool inside = x < gp.x1 && y < gp.y1;
     const size_t n = (size_t)gp.W * gp.H;
     const size_t i = inside ? (size_t)y * gp.W + x : 0;
@@ -275,13 +296,10 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
 
     const uint32_t total = *vplCount;
     const uint32_t per = (total + gp.numChunks - 1) / gp.numChunks;
-    const uint32_t begin = min(total, blockIdx.z * per);
+    const uint32_t begin = min(total, bz * per);
     const uint32_t end = __any_sync(0xffffffffu, valid) ? min(total, begin + per) : begin;
 
     V3 result = v3s(0.0f);
-    unsigned rays = 0;
-    unsigned shaftCnt[3] = {0u, 0u, 0u}, shaftSteps = 0u;
-    int ovf = 0;
     for (uint32_t base = begin; base < end; base += GATHER_BATCH) {
         const uint32_t nb = min((uint32_t)GATHER_BATCH, end - base);
         __syncwarp();
@@ -324,22 +342,25 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
             }
         }
     }
+    if (inside) {
+        const V3 out = result * gp.invNumVpl;  // result / (float)numVplLightPaths (reciprocal multiply, lighttracing.cu:378)
+        const long long q[3] = {to_fixed(out.x), to_fixed(out.y), to_fixed(out.z)};
+        if (gp.numChunks == 1) {
+            for (int c = 0; c < 3; c++) acc[i * 3 + c] = gp.doAccumulate ? acc[i * 3 + c] + q[c] : q[c];
+        } else {
+            // (the tile was cleared beforehand when doAccumulate == 0)
+            for (int c = 0; c < 3; c++)
+                if (q[c]) atomicAdd(reinterpret_cast<unsigned long long*>(acc + i * 3 + c), (unsigned long long)q[c]);
+        }
+    }
+    if (!gp.persistent) break;
+    }  // next tile
     if (ovf) stats->stackOverflow = 1;
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
     if (lane == 0 && rays) atomicAdd(&stats->shadowRays, (unsigned long long)rays);
     if (SHAFT && lane == 0 && shaftSteps) {
         atomicAdd(&stats->shaftSteps, (unsigned long long)shaftSteps); atomicAdd(&stats->shaftFallbacks, (unsigned long long)shaftCnt[0]);
         atomicAdd(&stats->shaftNodeVisits, (unsigned long long)shaftCnt[1]); atomicAdd(&stats->shaftCandLeaves, (unsigned long long)shaftCnt[2]);
-    }
-    if (!inside) return;
-    const V3 out = result * gp.invNumVpl;  // result / (float)numVplLightPaths (reciprocal multiply, lighttracing.cu:378)
-    const long long q[3] = {to_fixed(out.x), to_fixed(out.y), to_fixed(out.z)};
-    if (gp.numChunks == 1) {
-        for (int c = 0; c < 3; c++) acc[i * 3 + c] = gp.doAccumulate ? acc[i * 3 + c] + q[c] : q[c];
-    } else {
-        // (the tile was cleared beforehand when doAccumulate == 0)
-        for (int c = 0; c < 3; c++)
-            if (q[c]) atomicAdd(reinterpret_cast<unsigned long long*>(acc + i * 3 + c), (unsigned long long)q[c]);
     }
 }
 
@@ -1043,6 +1064,7 @@ extern int g_splatGroup;       // capi.cu: lanes per photon in the scatter splat
 extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatter splat
 extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
 extern int g_shaftCandMax;     // capi.cu
+extern int g_gatherPersistent;
 extern int g_gatherMode;       // capi.cu: 0 = per-ray packet traversal, 1 = shaft traversal of the 32-wide hierarchy
 extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
 
@@ -1121,22 +1143,33 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         clear_tile_kernel<<<cg, 128, 0, c->stream>>>(c->accVpl.p, c->W, t.x0, t.y0, t.x1, t.y1);
         c->launches++;
     }
+    g.vgx = grid.x; g.vgy = grid.y; g.vgz = grid.z;
+    g.persistent = g_gatherPersistent;
+    uint32_t* tileCounter = c->counters.p + 2;  // (slots 0-2 belong to the BVH build, which is over by now)
+    dim3 lgrid = grid;
+    if (g.persistent) {
+        e = cudaMemsetAsync(tileCounter, 0, sizeof(uint32_t), c->stream);
+        if (e != cudaSuccess) return e;
+        const unsigned resident = 148u * 5u;  // at most 5 blocks of 256 threads fit an SM at any register count used here
+        const unsigned blocks = grid.x * grid.y * grid.z;
+        lgrid = dim3(blocks < resident ? blocks : resident, 1, 1);
+    }
     c->stageBegin(ST_GATHER);
     if (g_gatherMode >= 1) {
         const int mb = g_gatherMinBlocks ? g_gatherMinBlocks : 4;  // measured: 64 registers / 4 blocks per SM wins by 5 % here
         if (mb == 2)
-            gather_vpl_kernel<2, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+            gather_vpl_kernel<2, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
         else if (mb == 5)
-            gather_vpl_kernel<5, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+            gather_vpl_kernel<5, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
         else if (mb == 4)
-            gather_vpl_kernel<4, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+            gather_vpl_kernel<4, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
         else
-            gather_vpl_kernel<3, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p);
+            gather_vpl_kernel<3, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
     } else {
         switch (g_gatherMinBlocks) {
-            case 2: gather_vpl_kernel<2, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
-            case 4: gather_vpl_kernel<4, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
-            default: gather_vpl_kernel<3, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p); break;
+            case 2: gather_vpl_kernel<2, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter); break;
+            case 4: gather_vpl_kernel<4, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter); break;
+            default: gather_vpl_kernel<3, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter); break;
         }
     }
     c->stageEnd(ST_GATHER);

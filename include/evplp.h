@@ -259,6 +259,8 @@ int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
  * "gather_mode": 1 (default) = the warp descends a 32-wide hierarchy with one conservative shaft-vs-box test per child
  * and runs the exact per-ray triangle tests on the collected candidate leaves; 0 = per-ray packet traversal of the 4-wide
  * hierarchy; 2 = shaft traversal in the VSL gather too (sampling-bound: no gain measured).  "shaft_max_candidates" (candidate leaves per step before falling back to mode 0, <= 128, default 96),
+ * "gather_persistent" (default 1: one resident wave of blocks whose warps draw 8x4-pixel tiles from a global counter; 0 = one
+ * tile per warp of a full grid),
  * "bvh_leaf_max" / "shaft_leaf_max" (before evplp_build_bvh), "gather_min_blocks", "splat_mode" (0 tiled, 1 scatter),
  * "splat_group", "splat_max_entries": kernel variants.  Options are process-wide; the handle may be NULL. */
 int evplp_set_option(evplp_handle h, const char* name, int value);

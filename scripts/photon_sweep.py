@@ -25,7 +25,10 @@ for paths in sizes:
     capi.check(lib, lib.evplp_synchronize(h), "sync")
     dt = (time.perf_counter() - t0) / reps
     st = capi.Stats(); capi.check(lib, lib.evplp_stats(h, C.byref(st)), "stats")
+    ms = C.c_float(); stage = {}
+    for name, idx in (("light_trace", 2), ("photon_splat", 4)):   # the LAST chunk of the frame (evplp_last_stage_ms)
+        capi.check(lib, lib.evplp_last_stage_ms(h, idx, C.byref(ms)), "stage_ms"); stage[name] = round(ms.value, 3)
     print(json.dumps({"res": f"{W}x{H}", "paths": paths, "records_per_frame": paths * 4, "frame_ms": round(dt * 1e3, 2),
                       "paths_per_s": paths / dt, "records_per_s": paths * 4 / dt, "usable_photons_per_s": st.splatPhotons / reps / dt,
-                      "fragments_per_s": st.splatFragments / reps / dt, "radius": t.state()["radius"]}))
+                      "fragments_per_s": st.splatFragments / reps / dt, "radius": t.state()["radius"], "last_chunk_stage_ms": stage}))
     t.close()
