@@ -17,7 +17,8 @@ int g_splatGroup = 0;
 int g_bvhLeafMax = BVH_LEAF_MAX;
 int g_shaftLeafMax = 2;
 int g_gatherMode = 1;   // 1 = shaft traversal of the 32-wide hierarchy (default), 0 = per-ray packet traversal
-int g_shaftCandMax = 96;
+int g_shaftCandMax = 128;
+int g_shaftStreak = 3, g_shaftSkip = 256;  // shaft_streak / shaft_skip: see GatherParams
 int g_gatherPersistent = 1;   // gather_persistent: warps draw 8x4-pixel tiles from a global counter (0 = one tile per warp of the grid)
 int g_splatMode = 0;
 int g_splatMaxEntries = 256 * 1024 * 1024;
@@ -629,6 +630,8 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
     if (strcmp(name, "bvh_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "bvh_leaf_max must be 1..8"); evplp::g_bvhLeafMax = value; return EVPLP_OK; }
     if (strcmp(name, "shaft_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "shaft_leaf_max must be 1..8"); evplp::g_shaftLeafMax = value; return EVPLP_OK; }
     if (strcmp(name, "shaft_max_candidates") == 0) { evplp::g_shaftCandMax = value; return EVPLP_OK; }
+    if (strcmp(name, "shaft_streak") == 0) { evplp::g_shaftStreak = value; return EVPLP_OK; }
+    if (strcmp(name, "shaft_skip") == 0) { evplp::g_shaftSkip = value; return EVPLP_OK; }
     if (strcmp(name, "gather_persistent") == 0) { evplp::g_gatherPersistent = value != 0; return EVPLP_OK; }
     if (strcmp(name, "gather_mode") == 0) { evplp::g_gatherMode = value; return EVPLP_OK; }
     if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }

@@ -442,7 +442,8 @@ __device__ __forceinline__ bool shaft_overlap(const Shaft& s, float blx, float b
 __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 org, V3 dir, float tmin, float tmax, const Shaft& sh,
                                             uint32_t stackBase, uint32_t candBase, uint32_t* warpStack,
                                             int candMax /* more candidate leaves than this => per-ray packet traversal */, int* overflow,
-                                            unsigned* counters /* [0] fallbacks [1] node visits [2] candidate leaves (per warp) */) {
+                                            unsigned* counters /* [0] fallbacks [1] node visits [2] candidate leaves (per warp) */,
+                                            bool forcePacket = false /* skip the descent: the caller expects it to overflow */) {
     const unsigned full = 0xffffffffu;
     if (sc.numShaftNodes == 0 || !__any_sync(full, active)) return false;
     const uint32_t lane = threadIdx.x & 31u;
@@ -452,8 +453,8 @@ __device__ inline bool trace_any_warp_shaft(const DevScene& sc, bool active, V3 
     uint32_t sp = stackBase, cp = candBase;
     const uint32_t spEnd = stackBase + 4u * BVH_STACK, cpEnd = candBase + 4u * (uint32_t)candMax;
     uint32_t cur = 0;
-    bool fallback = false;
-    while (true) {
+    bool fallback = forcePacket;
+    while (!forcePacket) {
         counters[1]++;
         const uint32_t idx = cur * NODE_F + lane;
         const uint32_t word = __float_as_uint(__ldg(base + idx + 6 * SHAFT_WIDTH));

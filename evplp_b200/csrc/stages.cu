@@ -242,6 +242,7 @@ struct GatherParams {
     // whose tile is cheap (culled by the cosine test, sky) go on to new work instead of idling until their block ends.
     unsigned vgx, vgy, vgz;
     int persistent;
+    int shaftStreak, shaftSkip;  // shaft gather: overflows in a row before, and number of, steps sent straight to the packet traversal
 };
 
 template <int MINB, bool SHAFT>
@@ -300,6 +301,7 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     const uint32_t end = __any_sync(0xffffffffu, valid) ? min(total, begin + per) : begin;
 
     V3 result = v3s(0.0f);
+    int streak = 0, skipLeft = 0;
     for (uint32_t base = begin; base < end; base += GATHER_BATCH) {
         const uint32_t nb = min((uint32_t)GATHER_BATCH, end - base);
         __syncwarp();
@@ -327,9 +329,20 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
             // Ray(vpl.pos, -v12, shadow, 0.0001, 1 - 0.0001) -- lighttracing.cu:292
             bool occluded;
             if (SHAFT) {
+                // Overflowing shafts come in runs (a tile in clutter or across a depth edge overflows towards most VPLs):
+                // after shaftStreak overflows in a row the next shaftSkip steps go to the packet traversal directly
+                // instead of paying for a descent that is expected to be thrown away.
+                const bool any = __any_sync(0xffffffffu, active);
                 const Shaft sh = make_shaft(vpos, tileLo, tileHi);
-                occluded = trace_any_warp_shaft(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stackBase, candBase, stacks[warp], gp.shaftCandMax, &ovf, shaftCnt);
-                shaftSteps += __any_sync(0xffffffffu, active) ? 1u : 0u;
+                const unsigned before = shaftCnt[0];
+                occluded = trace_any_warp_shaft(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), sh, stackBase, candBase, stacks[warp], gp.shaftCandMax, &ovf, shaftCnt,
+                                                skipLeft > 0);
+                if (any) {
+                    shaftSteps++;
+                    if (skipLeft > 0) skipLeft--;
+                    else if (shaftCnt[0] != before) { if (++streak >= gp.shaftStreak) { skipLeft = gp.shaftSkip; streak = 0; } }
+                    else streak = 0;
+                }
             } else {
                 occluded = trace_any_warp(sc, active, vpos, -v12, (float)0.0001, (float)(1 - 0.0001), stacks[warp], &ovf);
             }
@@ -1065,6 +1078,7 @@ extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatte
 extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
 extern int g_shaftCandMax;     // capi.cu
 extern int g_gatherPersistent;
+extern int g_shaftStreak, g_shaftSkip;
 extern int g_gatherMode;       // capi.cu: 0 = per-ray packet traversal, 1 = shaft traversal of the 32-wide hierarchy
 extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
 
@@ -1145,6 +1159,8 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     }
     g.vgx = grid.x; g.vgy = grid.y; g.vgz = grid.z;
     g.persistent = g_gatherPersistent;
+    g.shaftStreak = g_shaftStreak > 0 ? g_shaftStreak : 1;
+    g.shaftSkip = g_shaftSkip;
     uint32_t* tileCounter = c->counters.p + 2;  // (slots 0-2 belong to the BVH build, which is over by now)
     dim3 lgrid = grid;
     if (g.persistent) {

@@ -258,7 +258,8 @@ int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
  * tile -- the interleaved image partition of a single heavy frame over N GPUs (stride = N, offset = rank).
  * "gather_mode": 1 (default) = the warp descends a 32-wide hierarchy with one conservative shaft-vs-box test per child
  * and runs the exact per-ray triangle tests on the collected candidate leaves; 0 = per-ray packet traversal of the 4-wide
- * hierarchy; 2 = shaft traversal in the VSL gather too (sampling-bound: no gain measured).  "shaft_max_candidates" (candidate leaves per step before falling back to mode 0, <= 128, default 96),
+ * hierarchy; 2 = shaft traversal in the VSL gather too (sampling-bound: no gain measured).  "shaft_max_candidates" (candidate leaves per step before falling back to mode 0, <= 128 = default),
+ * "shaft_streak" / "shaft_skip" (after 3 overflowing steps in a row a warp sends its next 256 steps straight to the packet traversal: overflow is a property of the tile),
  * "gather_persistent" (default 1: one resident wave of blocks whose warps draw 8x4-pixel tiles from a global counter; 0 = one
  * tile per warp of a full grid),
  * "bvh_leaf_max" / "shaft_leaf_max" (before evplp_build_bvh), "gather_min_blocks", "splat_mode" (0 tiled, 1 scatter),
