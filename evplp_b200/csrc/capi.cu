@@ -19,6 +19,7 @@ int g_shaftLeafMax = 2;
 int g_gatherMode = 1;   // 1 = shaft traversal of the 32-wide hierarchy (default), 0 = per-ray packet traversal
 int g_shaftCandMax = 128;
 int g_shaftStreak = 3, g_shaftSkip = 256;  // shaft_streak / shaft_skip: see GatherParams
+int g_gatherLpt = 1;          // gather_lpt: persistent warps draw the tiles that were most expensive in the previous launch first
 int g_gatherPersistent = 1;   // gather_persistent: warps draw 8x4-pixel tiles from a global counter (0 = one tile per warp of the grid)
 int g_splatMode = 0;
 int g_splatMaxEntries = 256 * 1024 * 1024;
@@ -120,6 +121,7 @@ int evplp_destroy(evplp_handle c) {
     c->primIds.release(); c->primIdsSorted.release(); c->left.release(); c->right.release(); c->parent.release();
     c->leafParent.release(); c->rangeFirst.release(); c->rangeLast.release(); c->nodeBounds.release();
     c->refitFlags.release(); c->nodes.release(); c->shaftNodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
+    c->gatherCost.release(); c->gatherCostSorted.release(); c->gatherIota.release(); c->gatherOrder.release();
     c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->records.release();
     c->vplList.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
     c->accPhoton.release(); c->accLight.release(); c->resolveOut.release(); c->devStats.release();
@@ -632,6 +634,7 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
     if (strcmp(name, "shaft_max_candidates") == 0) { evplp::g_shaftCandMax = value; return EVPLP_OK; }
     if (strcmp(name, "shaft_streak") == 0) { evplp::g_shaftStreak = value; return EVPLP_OK; }
     if (strcmp(name, "shaft_skip") == 0) { evplp::g_shaftSkip = value; return EVPLP_OK; }
+    if (strcmp(name, "gather_lpt") == 0) { evplp::g_gatherLpt = value != 0; return EVPLP_OK; }
     if (strcmp(name, "gather_persistent") == 0) { evplp::g_gatherPersistent = value != 0; return EVPLP_OK; }
     if (strcmp(name, "gather_mode") == 0) { evplp::g_gatherMode = value; return EVPLP_OK; }
     if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }

@@ -101,6 +101,12 @@ struct EvplpContext {
     evplp::DevBuf<float> resolveOut;              // W*H*3
     float* resolvePinned = nullptr;
 
+    // VPL gather work order: cycles every 8x4-pixel tile took in the previous launch of the same grid (a progressive run
+    // renders the same view again and again), sorted so that the next launch draws the expensive tiles first
+    evplp::DevBuf<uint32_t> gatherCost, gatherCostSorted, gatherIota, gatherOrder;
+    uint64_t gatherSig[4] = {0, 0, 0, 0};          // launch grid + tile + band signature the costs belong to
+    bool gatherCostValid = false;
+
     evplp::DevBuf<evplp::DevStats> devStats;
     EvplpStats stats;
 

@@ -10,6 +10,7 @@
 //   resolve_kernel       replaces runFinalProgram + final.frag                     (rtcomphoton.h:756-787)
 //
 // Compiled with -fmad=false: all shading arithmetic rounds exactly as written (shading.h).
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -249,7 +250,8 @@ template <int MINB, bool SHAFT>
 __global__ void __launch_bounds__(GATHER_WARPS * 32, MINB)
 gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf, const EvplpRecord* __restrict__ records,
                   const uint32_t* __restrict__ vplList, const uint32_t* __restrict__ vplCount, long long* __restrict__ acc,
-                  DevStats* stats, uint32_t* __restrict__ tileCounter) {
+                  DevStats* stats, uint32_t* __restrict__ tileCounter, const uint32_t* __restrict__ tileOrder,
+                  uint32_t* __restrict__ tileCost) {
     // Every warp stages its own VPL batches (no block-wide barrier: warps whose pixels are
     // culled by the cosine test run ahead instead of waiting for the slowest warp of the block).
     // per VPL: the 6 float4 of its record + 3 float4 of shading terms that depend on the VPL alone (VplPre)
@@ -272,9 +274,11 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
         if (lane == 0) v = atomicAdd(tileCounter, 1u);
         v = __shfl_sync(0xffffffffu, v, 0);
         if (v >= vTotal) break;
+        if (tileOrder) v = __ldg(tileOrder + v);  // most expensive tiles of the previous launch first
     } else {
         v = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * GATHER_WARPS + warp;
     }
+    const long long itemStart = clock64();
     const uint32_t vw = v % GATHER_WARPS, vb = v / GATHER_WARPS;
     const uint32_t bx = vb % gp.vgx, by = (vb / gp.vgx) % gp.vgy, bz = vb / (gp.vgx * gp.vgy);
     const int x = gp.x0 + bx * 16 + (vw & 1) * 8 + (lane & 7);
@@ -367,6 +371,10 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
         }
     }
     if (!gp.persistent) break;
+    if (tileCost && lane == 0) {
+        const long long dt = (clock64() - itemStart) >> 8;
+        tileCost[v] = dt > 0xffffffffll ? 0xffffffffu : (uint32_t)dt;
+    }
     }  // next tile
     if (ovf) stats->stackOverflow = 1;
     for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
@@ -1048,6 +1056,11 @@ static cudaError_t compact_records(EvplpContext* c, uint64_t first, uint64_t cou
     return e;
 }
 
+__global__ void iota_kernel(uint32_t* out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
 // ------------------------------------------------------------------ launchers -----------
 cudaError_t launch_gbuffer(EvplpContext* c) {
     dim3 grid((c->W + 15) / 16, (c->H + 7) / 8);
@@ -1078,6 +1091,7 @@ extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatte
 extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
 extern int g_shaftCandMax;     // capi.cu
 extern int g_gatherPersistent;
+extern int g_gatherLpt;
 extern int g_shaftStreak, g_shaftSkip;
 extern int g_gatherMode;       // capi.cu: 0 = per-ray packet traversal, 1 = shaft traversal of the 32-wide hierarchy
 extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
@@ -1163,9 +1177,41 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     g.shaftSkip = g_shaftSkip;
     uint32_t* tileCounter = c->counters.p + 2;  // (slots 0-2 belong to the BVH build, which is over by now)
     dim3 lgrid = grid;
+    const uint32_t* tileOrder = nullptr;
+    uint32_t* tileCost = nullptr;
     if (g.persistent) {
         e = cudaMemsetAsync(tileCounter, 0, sizeof(uint32_t), c->stream);
         if (e != cudaSuccess) return e;
+        if (g_gatherLpt) {
+            // longest-processing-time-first: order the tiles by the cycles they took in the previous launch of this grid
+            const uint32_t vTotal = grid.x * grid.y * grid.z * GATHER_WARPS;
+            const uint64_t sig[4] = {((uint64_t)grid.x << 40) | ((uint64_t)grid.y << 20) | grid.z,
+                                     ((uint64_t)(uint32_t)t.x0 << 32) | (uint32_t)t.y0, ((uint64_t)(uint32_t)t.x1 << 32) | (uint32_t)t.y1,
+                                     ((uint64_t)(uint32_t)g.bandStride << 32) | (uint32_t)g.bandOffset};
+            const bool same = c->gatherCostValid && memcmp(sig, c->gatherSig, sizeof(sig)) == 0;
+            if (!same) {
+                if ((e = c->gatherCost.reserve(vTotal)) != cudaSuccess) return e;
+                if ((e = c->gatherCostSorted.reserve(vTotal)) != cudaSuccess) return e;
+                if ((e = c->gatherIota.reserve(vTotal)) != cudaSuccess) return e;
+                if ((e = c->gatherOrder.reserve(vTotal)) != cudaSuccess) return e;
+                iota_kernel<<<(vTotal + 255) / 256, 256, 0, c->stream>>>(c->gatherIota.p, vTotal);
+                c->launches++;
+                memcpy(c->gatherSig, sig, sizeof(sig));
+                c->gatherCostValid = true;
+            } else {
+                size_t tempBytes = 0;
+                e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tempBytes, c->gatherCost.p, c->gatherCostSorted.p, c->gatherIota.p,
+                                                              c->gatherOrder.p, (int)vTotal, 0, 32, c->stream);
+                if (e != cudaSuccess) return e;
+                if ((e = c->sortTemp.reserve(tempBytes)) != cudaSuccess) return e;
+                e = cub::DeviceRadixSort::SortPairsDescending(c->sortTemp.p, tempBytes, c->gatherCost.p, c->gatherCostSorted.p, c->gatherIota.p,
+                                                              c->gatherOrder.p, (int)vTotal, 0, 32, c->stream);
+                if (e != cudaSuccess) return e;
+                c->launches += 2;
+                tileOrder = c->gatherOrder.p;
+            }
+            tileCost = c->gatherCost.p;
+        }
         const unsigned resident = 148u * 5u;  // at most 5 blocks of 256 threads fit an SM at any register count used here
         const unsigned blocks = grid.x * grid.y * grid.z;
         lgrid = dim3(blocks < resident ? blocks : resident, 1, 1);
@@ -1174,18 +1220,18 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     if (g_gatherMode >= 1) {
         const int mb = g_gatherMinBlocks ? g_gatherMinBlocks : 4;  // measured: 64 registers / 4 blocks per SM wins by 5 % here
         if (mb == 2)
-            gather_vpl_kernel<2, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
+            gather_vpl_kernel<2, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost);
         else if (mb == 5)
-            gather_vpl_kernel<5, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
+            gather_vpl_kernel<5, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost);
         else if (mb == 4)
-            gather_vpl_kernel<4, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
+            gather_vpl_kernel<4, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost);
         else
-            gather_vpl_kernel<3, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter);
+            gather_vpl_kernel<3, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost);
     } else {
         switch (g_gatherMinBlocks) {
-            case 2: gather_vpl_kernel<2, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter); break;
-            case 4: gather_vpl_kernel<4, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter); break;
-            default: gather_vpl_kernel<3, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter); break;
+            case 2: gather_vpl_kernel<2, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost); break;
+            case 4: gather_vpl_kernel<4, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost); break;
+            default: gather_vpl_kernel<3, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost); break;
         }
     }
     c->stageEnd(ST_GATHER);

@@ -261,7 +261,8 @@ int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
  * hierarchy; 2 = shaft traversal in the VSL gather too (sampling-bound: no gain measured).  "shaft_max_candidates" (candidate leaves per step before falling back to mode 0, <= 128 = default),
  * "shaft_streak" / "shaft_skip" (after 3 overflowing steps in a row a warp sends its next 256 steps straight to the packet traversal: overflow is a property of the tile),
  * "gather_persistent" (default 1: one resident wave of blocks whose warps draw 8x4-pixel tiles from a global counter; 0 = one
- * tile per warp of a full grid),
+ * tile per warp of a full grid), "gather_lpt" (default 1: the tiles are drawn in descending order of the cycles they took in the
+ * previous launch of the same grid -- longest processing time first; results do not depend on the order),
  * "bvh_leaf_max" / "shaft_leaf_max" (before evplp_build_bvh), "gather_min_blocks", "splat_mode" (0 tiled, 1 scatter),
  * "splat_group", "splat_max_entries": kernel variants.  Options are process-wide; the handle may be NULL. */
 int evplp_set_option(evplp_handle h, const char* name, int value);
