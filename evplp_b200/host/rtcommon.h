@@ -223,10 +223,30 @@ struct RtScene {
             if (key == "Kd") ss >> e.kd[0] >> e.kd[1] >> e.kd[2];
             else if (key == "Ks") ss >> e.ks[0] >> e.ks[1] >> e.ks[2];
             else if (key == "Ns") ss >> e.ns;
-            else if (key == "map_Kd") ss >> e.mapKd;
-            else if (key == "map_Ks") ss >> e.mapKs;
-            else if (key == "map_Ns") ss >> e.mapNs;
+            else if (key == "map_Kd") e.mapKd = parse_map(ss);
+            else if (key == "map_Ks") e.mapKs = parse_map(ss);
+            else if (key == "map_Ns") e.mapNs = parse_map(ss);
         }
+    }
+
+    // "map_Kd [-option args ...] file name": Assimp's ObjFileMtlImporter::getTexture skips the texture options and takes the
+    // rest of the line as the file name (it may contain spaces); files written on Windows use backslashes.
+    static std::string parse_map(std::istringstream& ss) {
+        std::vector<std::string> tok;
+        std::string t;
+        while (ss >> t) tok.push_back(t);
+        auto numeric = [](const std::string& v) { char* e; strtod(v.c_str(), &e); return e != v.c_str() && *e == 0; };
+        size_t i = 0;
+        while (i < tok.size() && tok[i].size() > 1 && tok[i][0] == '-' && !numeric(tok[i])) {
+            const std::string& o = tok[i++];
+            if (o == "-o" || o == "-s" || o == "-t") { int n = 0; while (n < 3 && i < tok.size() && numeric(tok[i])) { i++; n++; } }
+            else if (o == "-mm") i += 2;
+            else i += 1;  // -blendu -blendv -cc -clamp -bm -boost -texres -imfchan -type: one argument
+        }
+        std::string name;
+        for (; i < tok.size(); i++) name += (name.empty() ? "" : " ") + tok[i];
+        for (char& c : name) if (c == '\\') c = '/';
+        return name;
     }
 
     static shared_ptr<RtTexture> load_texture(const std::string& filedir, const std::string& map, const float* rgb, bool shininess) {
@@ -262,15 +282,18 @@ struct RtScene {
         int curMat = 0;  // 0 = DefaultMaterial
         std::string line;
         while (std::getline(f, line)) {
+            const size_t lead = line.find_first_not_of(" \t");
+            if (lead == std::string::npos) continue;
+            if (lead) line.erase(0, lead);
             if (line.size() < 2) continue;
-            if (line[0] == 'v' && line[1] == ' ') {
+            if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
                 float x, y, z;
                 if (sscanf(line.c_str() + 2, "%f %f %f", &x, &y, &z) == 3) { pos.push_back(x); pos.push_back(y); pos.push_back(z); }
             } else if (line[0] == 'v' && line[1] == 't') {
                 float u = 0, v = 0;
                 sscanf(line.c_str() + 3, "%f %f", &u, &v);
                 uv.push_back(u); uv.push_back(v);
-            } else if (line[0] == 'f' && line[1] == ' ') {
+            } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
                 auto key = std::make_pair(objectName, curMat);
                 auto it = builderOf.find(key);
                 if (it == builderOf.end()) {
@@ -326,9 +349,11 @@ struct RtScene {
                 curMat = 0;
                 for (size_t m = 0; m < mtl.size(); m++) if (mtl[m].name == name) curMat = (int)m + 1;
             } else if (line.compare(0, 6, "mtllib") == 0) {
-                std::istringstream ss(line.substr(6));
-                std::string name;
-                ss >> name;
+                // the rest of the line is the file name (it may contain spaces)
+                std::string name = line.substr(6);
+                const size_t a = name.find_first_not_of(" \t"), b = name.find_last_not_of(" \t\r\n");
+                name = a == std::string::npos ? std::string() : name.substr(a, b - a + 1);
+                for (char& ch : name) if (ch == '\\') ch = '/';
                 load_mtl(filedir + name, mtl);
             } else if ((line[0] == 'o' || line[0] == 'g') && line[1] == ' ') {
                 std::istringstream ss(line.substr(2));
