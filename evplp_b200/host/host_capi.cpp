@@ -193,6 +193,52 @@ float evplp_host_pfm_relmse(const char* a, const char* b) {
 }
 
 
+// Host-only configuration check: reads a scene JSON file exactly as main.cpp / LoadScene / the techniques' parse() do, but
+// against an already built scene (the OBJ files a reference JSON names may be absent), and reports what was understood.
+// out[0..2] = sections present (pt, photonfam, lvcphotonfam); out[3..4] = resX, resY; out[5..13] = camera origin, look-at,
+// up; out[14] = fovy (radians); per family section f (base 16 for photonfam, 40 for lvcphotonfam): numLightPaths,
+// numVplLightPaths, numMaxBounces, radiusPercentage, misMode, DoProgressive, AlphaProgressive, forceVsl, vplSplat on,
+// photonSplat on, frameMode, rngOffset, numMaxIteration, timeLimitMs, clampingValue, vslRadiusPercentage, useJitter;
+// pt (base 64): rngOffset, numMaxIteration, timeLimitMs, numMaxBounces, numSamplePerPixel, frameMode, useJitter.
+int evplp_host_config_check(void* s, const char* jsonPath, double out[80]) {
+    GUARD(
+        HostScene* hs = (HostScene*)s;
+        std::ifstream ifs(jsonPath);
+        if (!ifs.is_open()) throw std::runtime_error(std::string("cannot open ") + jsonPath);
+        std::stringstream buf; buf << ifs.rdbuf();
+        const Json json = Json::parse(buf.str());
+        for (int i = 0; i < 80; i++) out[i] = 0.0;
+        Vec2 res; res.x = json.at("resX").as_float(); res.y = json.at("resY").as_float();
+        out[3] = res.x; out[4] = res.y;
+        const Json& cj = json.contains("camera") ? json["camera"] : json.at("stablecamera");
+        RtStableCamera cam(cj, res.x / res.y);
+        out[5] = cam.mOrigin.x; out[6] = cam.mOrigin.y; out[7] = cam.mOrigin.z;
+        out[8] = cam.mLookAt.x; out[9] = cam.mLookAt.y; out[10] = cam.mLookAt.z;
+        out[11] = cam.mUp.x; out[12] = cam.mUp.y; out[13] = cam.mUp.z; out[14] = cam.mFovy;
+        const char* fam[2] = {"photonfam", "lvcphotonfam"};
+        for (int f = 0; f < 2; f++) {
+            if (!json.contains(fam[f]) || json[fam[f]].is_null()) continue;
+            out[1 + f] = 1.0;
+            std::unique_ptr<RtComPhoton> t(f ? new RtLvcComPhoton(0) : new RtComPhoton(0));
+            t->parse(hs->scene, res, json[fam[f]]);
+            double* o = out + 16 + 24 * f;
+            o[0] = t->mNumLightPaths; o[1] = t->mNumVplLightPaths; o[2] = t->mNumMaxBounce; o[3] = t->mRadiusPercentage;
+            o[4] = (double)t->mMisMode; o[5] = t->mDoProgressive; o[6] = t->mAlphaProgressive; o[7] = t->mForceVsl;
+            o[8] = t->mDoVplSplat; o[9] = t->mDoPhotonSplat; o[10] = (double)t->mFrameMode; o[11] = t->mRngOffset;
+            o[12] = t->mNumMaxIteration; o[13] = t->mTimelimitMs; o[14] = t->mClampingValue; o[15] = t->mVslRadiusPercentage;
+            o[16] = t->mJitter;
+        }
+        if (json.contains("pt") && !json["pt"].is_null()) {
+            out[0] = 1.0;
+            RtPt2 t(0);
+            t.parse(hs->scene, res, json["pt"]);
+            double* o = out + 64;
+            o[0] = t.mRngOffset; o[1] = t.mNumMaxIteration; o[2] = t.mTimelimitMs; o[3] = t.mNumMaxBounce; o[4] = t.mNumSamplePerPixel;
+            o[5] = (double)t.mFrameMode; o[6] = t.mJitter;
+        }
+        return 0;)
+}
+
 // texture decoding taps: a JPEG byte stream -> top-down RGB8 (what stbi_load(path, .., 3) returns without the
 // flip), and a texture file -> the RGBA32F texels RtTexture hands to evplp_upload_scene
 int evplp_host_jpeg_info(const uint8_t* data, uint64_t n, int32_t* width, int32_t* height, int32_t* fileChannels) {

@@ -57,6 +57,7 @@ def load_host_library():
     lib.evplp_host_save_pfm.argtypes = [C.c_char_p, _P, C.c_int, C.c_int]
     lib.evplp_host_pfm_relmse.restype = C.c_float
     lib.evplp_host_pfm_relmse.argtypes = [C.c_char_p, C.c_char_p]
+    lib.evplp_host_config_check.argtypes = [_P, C.c_char_p, C.POINTER(C.c_double)]
     lib.evplp_host_jpeg_info.argtypes = [_P, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.evplp_host_jpeg_decode.argtypes = [_P, C.c_uint64, _P, C.c_uint64]
     lib.evplp_host_texture_load.argtypes = [C.c_char_p, C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.c_uint64]
@@ -242,6 +243,29 @@ def export_scene(name, out_dir, seed=1, detail=8, res_x=1280, res_y=720):
     lib = load_host_library()
     if lib.evplp_host_export_scene(name.encode(), out_dir.encode(), seed, detail, res_x, res_y) != 0:
         _err(lib, "evplp_host_export_scene")
+
+
+MIS_NAMES = ("one", "balance", "max", "power2", "geometryClamp", "geometryBrdfClamp")
+_FAM_KEYS = ("numLightPaths", "numVplLightPaths", "numMaxBounces", "radiusPercentage", "misMode", "DoProgressive", "AlphaProgressive",
+             "forceVsl", "vplSplat", "photonSplat", "frameMode", "rngOffset", "numMaxIteration", "timeLimitMs", "clampingValue",
+             "vslRadiusPercentage", "useJitter")
+_PT_KEYS = ("rngOffset", "numMaxIteration", "timeLimitMs", "numMaxBounces", "numSamplePerPixel", "frameMode", "useJitter")
+
+
+def config_check(host_scene, json_path):
+    """What the C++ host (main.cpp dispatch, RtStableCamera, the techniques' parse()) understands of a scene JSON file,
+    evaluated against `host_scene` instead of the OBJ files the JSON names.  No device is touched."""
+    lib = load_host_library()
+    out = (C.c_double * 80)()
+    if lib.evplp_host_config_check(host_scene.h, json_path.encode(), out) != 0:
+        _err(lib, "evplp_host_config_check")
+    r = {"resX": out[3], "resY": out[4], "camera": {"origin": list(out[5:8]), "lookAt": list(out[8:11]), "up": list(out[11:14]), "fovy": out[14]}}
+    for f, name in enumerate(("photonfam", "lvcphotonfam")):
+        if out[1 + f]:
+            r[name] = dict(zip(_FAM_KEYS, out[16 + 24 * f:16 + 24 * f + len(_FAM_KEYS)]))
+    if out[0]:
+        r["pt"] = dict(zip(_PT_KEYS, out[64:64 + len(_PT_KEYS)]))
+    return r
 
 
 def decode_jpeg(data):
