@@ -180,6 +180,38 @@ def test_vpl_gather_all_mis_modes(rig, mis, gather_mode):
     assert (np.abs(a - b) <= 6 + 1e-5 * np.abs(b)).all()  # 1e-5 relative + a few Q31.32 quanta (one rounding per chunk)
 
 
+@pytest.mark.parametrize("chunks", [2, 5])
+def test_chunked_gather_equals_the_oracle_chunk_by_chunk(rig, chunks):
+    """gather_chunks = N (what balances small image shares in the multi-GPU image partition) splits the usable-VPL list into N
+    contiguous ranges of ceil(total / N); each range is summed in record order in float by one thread per pixel, scaled by
+    1 / numVplLightPaths, converted to Q31.32 and added with integer atomics.  That is deterministic, and it equals -- bit for
+    bit -- the oracle run on each range alone (IsUsableVpl cleared on every other record) with the fixed-point images added."""
+    P = rig.params(mis_mode=1, accumulate=False)
+    planes, prims, rec = _setup_iteration(rig, P)
+    prefix = int(P.numVplLightPaths) * int(P.numPhotonsPerLightPath)
+    usable = np.flatnonzero(rec["flags"][:prefix] & 1)
+    per = (len(usable) + chunks - 1) // chunks
+    eacc = np.zeros((H, W, 3), dtype=np.int64)
+    for c in range(chunks):
+        sub = rec.copy()
+        drop = np.ones(prefix, dtype=bool)
+        drop[usable[c * per:(c + 1) * per]] = False
+        flags = sub["flags"]
+        flags[:prefix][drop] &= np.uint32(0xFFFFFFFE)
+        sub["flags"] = flags
+        exp, _ = rig.orc.vpl_gather(P, W, H, planes, prims, sub, capi.GATHER_VPL)
+        rig.orc.accumulate_fixed(exp, eacc)
+    assert eacc.sum() > 0
+    rig.dev.set_option("gather_chunks", chunks)
+    try:
+        for _ in range(2):  # twice: the result does not depend on the order the atomics land in
+            rig.dev.vpl_gather(capi.GATHER_VPL)
+            vpl, _, _ = rig.dev.download_accum()
+            assert np.array_equal(vpl, eacc)
+    finally:
+        rig.dev.set_option("gather_chunks", 0)
+
+
 def test_vpl_gather_accumulates_and_tiles(rig):
     P = rig.params(mis_mode=4, accumulate=True)
     planes, prims, rec = _setup_iteration(rig, P)
