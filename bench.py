@@ -333,8 +333,8 @@ def run_gpu(args):
                          "frac": ach / fp32_peak, "traffic": traffic,
                          "note": f"{FLOP_PER_PAIR:.0f} algorithmic FP32 flop per pair (SURVEY 8d) x pairs / gather kernel time; peak = "
                                  f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz ({how} clock); the kernel is shadow-ray traversal bound, "
-                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v9_ncu_full_summary.txt: 65 % of peak "
-                                 "instruction issue, ALU pipe 41 %, FMA pipe 25 %, DRAM 0.03 %)" + traffic_src},
+                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v9_ncu_full_summary.txt: 68 % of peak "
+                                 "instruction issue, ALU pipe 43 %, FMA pipe 26 %, DRAM 0.04 %)" + traffic_src},
             "roofline_splat": {"kernel": "splat_prepare + splat_fill + splat_tile_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": None,
                                "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}"},
