@@ -253,7 +253,9 @@ int evplp_event_record(evplp_handle h, int slot);
 int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
 /* Tuning knobs (no reference counterpart).  "gather_chunks": number of slices the VPL list is
  * split into across thread blocks (0 = automatic; 1 = every pixel sums its VPLs in record
- * order in one thread, which makes the gather bit-identical to the scalar oracle).
+ * order in one thread, which makes the gather bit-identical to the scalar oracle; N > 1 = N contiguous ranges of
+ * ceil(total / N) usable VPLs, each summed in record order and added in Q31.32 with integer atomics: deterministic, and
+ * bit-identical to the oracle evaluated range by range).
  * "gather_band_stride" / "gather_band_offset": the gather only renders the 16-row bands b = offset (mod stride) of its
  * tile -- the interleaved image partition of a single heavy frame over N GPUs (stride = N, offset = rank).
  * "gather_mode": 1 (default) = the warp descends a 32-wide hierarchy with one conservative shaft-vs-box test per child
