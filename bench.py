@@ -112,12 +112,17 @@ def cpu_sample(steps, warmup, tile_w=32, tile_h=16):
     """Times the oracle on a BOUNDED sample of the workload: the full VPL set of one iteration
     gathered into a tile_w x tile_h pixel tile at the image centre (pairs/s does not depend on
     the tile size).  Returns (pairs_per_s, seconds_per_step, cores, description)."""
-    from evplp_b200 import host_api as HA, _capi as capi, scene as S
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the oracle gets all the host cores explicitly
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+    from evplp_b200 import host_api as HA, _capi as capi, scene as S   # ctypes declarations only: no library is loaded by the import
     from tests import oracle_api as O
 
-    hs = HA.HostScene.generate(SCENE, SEED, DETAIL, RES_X / RES_Y)
+    # the scene comes from libevplp_scene.so (host data preparation, links nothing of the product)
+    hs = HA.HostScene.generate(SCENE, SEED, DETAIL, RES_X / RES_Y, scene_only=True)
     sc = hs.to_scene()
     orc = O.OracleScene(sc)
+    O.load().orc_set_threads(ncpu)
     cores = O.load().orc_num_threads()
     cam = hs.camera()
     nvpl, npaths = PHOTONFAM["numVplLightPaths"], PHOTONFAM["numLightPaths"]

@@ -345,11 +345,9 @@ __global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const 
     nd.child[0] = bvh_make_leaf(0u, (uint32_t)n);
 }
 
-extern int g_bvhLeafMax;  // capi.cu: triangles per leaf child (1..8)
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (err) *err = std::string(#x) + ": " + cudaGetErrorString(e_); return e_; } } while (0)
 
-extern int g_shaftLeafMax;  // capi.cu: triangles per leaf child of the 32-wide hierarchy
 
 // Level-by-level collapse of the binary radix tree into W-ary nodes (surface-area guided: the child with
 // the largest box is opened first), leaves of <= leafMax triangles.
@@ -411,7 +409,7 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     CK(c->nodes.reserve(nInt > 0 ? nInt : 1));
     // 32-wide nodes: every bottom-level node covers > leafMax triangles of its own and every node with node children is
     // full (32 children), so there are at most ~n / (leafMax + 1) * 32/31 of them
-    CK(c->shaftNodes.reserve(nInt > 0 ? (size_t)nInt / (size_t)(g_shaftLeafMax + 1) + (size_t)nInt / 16 + 64 : 1));
+    CK(c->shaftNodes.reserve(nInt > 0 ? (size_t)nInt / (size_t)(c->opt.shaftLeafMax + 1) + (size_t)nInt / 16 + 64 : 1));
     CK(c->sceneBoundsEnc.reserve(6));
     CK(c->queueA.reserve(2 * (size_t)(nInt + 1))); CK(c->queueB.reserve(2 * (size_t)(nInt + 1)));
     CK(c->counters.reserve(4));
@@ -448,7 +446,7 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     // 4 leaf records
     leaf_records_kernel<<<gridN, TB, 0, st>>>(c->triVerts.p, c->primIdsSorted.p, n, c->triLeaf.p);
     c->launches++;
-    if (n <= g_bvhLeafMax) {
+    if (n <= c->opt.bvhLeafMax) {
         tiny_root_kernel<BVH_WIDTH><<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->nodes.p);
         tiny_root_kernel<SHAFT_WIDTH><<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->shaftNodes.p);
         c->launches += 2;
@@ -470,9 +468,9 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     c->launches++;
     // 7 collapse into the 4-wide per-ray hierarchy and the 32-wide shaft hierarchy
     {
-        cudaError_t e = run_collapse<BVH_WIDTH>(c, c->nodes.p, g_bvhLeafMax, &c->numNodes, err);
+        cudaError_t e = run_collapse<BVH_WIDTH>(c, c->nodes.p, c->opt.bvhLeafMax, &c->numNodes, err);
         if (e != cudaSuccess) return e;
-        e = run_collapse<SHAFT_WIDTH>(c, c->shaftNodes.p, g_shaftLeafMax, &c->numShaftNodes, err);
+        e = run_collapse<SHAFT_WIDTH>(c, c->shaftNodes.p, c->opt.shaftLeafMax, &c->numShaftNodes, err);
         if (e != cudaSuccess) return e;
     }
     CK(cudaGetLastError());

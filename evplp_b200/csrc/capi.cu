@@ -3,27 +3,16 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "context.h"
 
 using namespace evplp;
 
-namespace evplp {
-int g_gatherChunks = 0;
-int g_bandStride = 0, g_bandOffset = 0;
-int g_gatherMinBlocks = 0;   // 0 = per-mode default (shaft: 4 blocks/SM, packet: 3)
-int g_splatGroup = 0;
-int g_bvhLeafMax = BVH_LEAF_MAX;
-int g_shaftLeafMax = 2;
-int g_gatherMode = 1;   // 1 = shaft traversal of the 32-wide hierarchy (default), 0 = per-ray packet traversal
-int g_shaftCandMax = 128;
-int g_shaftStreak = 3, g_shaftSkip = 256;  // shaft_streak / shaft_skip: see GatherParams
-int g_gatherLpt = 1;          // gather_lpt: persistent warps draw the tiles that were most expensive in the previous launch first
-int g_gatherPersistent = 1;   // gather_persistent: warps draw 8x4-pixel tiles from a global counter (0 = one tile per warp of the grid)
-int g_splatMode = 0;
-int g_splatMaxEntries = 256 * 1024 * 1024;
-}
+// defaults a new handle starts from (evplp_set_option with a NULL handle); guarded: handles may be created from several threads
+static evplp::Options g_defaultOptions;
+static std::mutex g_defaultsMutex;
 
 static thread_local std::string g_err;
 
@@ -81,7 +70,10 @@ int evplp_create(int device, int width, int height, evplp_handle* out) {
     if (prop.major < 10) return fail(EVPLP_ERR_NO_DEVICE, "evplp_create: device is not sm_100 class (Blackwell B200 required)");
     CU(cudaSetDevice(device));
     EvplpContext* c = new EvplpContext();
+    { std::lock_guard<std::mutex> lock(g_defaultsMutex); c->opt = g_defaultOptions; }
     c->device = device; c->W = width; c->H = height;
+    // every failure below destroys the partially built context (stream, events, buffers) before returning
+    struct Guard { EvplpContext* c; ~Guard() { if (c) evplp_destroy(c); } } guard{c};
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int s = 0; s < ST_COUNT; s++) {
         CU(cudaEventCreate(&c->stageA[s]));
@@ -108,6 +100,7 @@ int evplp_create(int device, int width, int height, evplp_handle* out) {
     memset(&c->stats, 0, sizeof(c->stats));
     memset(&c->params, 0, sizeof(c->params));
     CU(cudaStreamSynchronize(c->stream));
+    guard.c = nullptr;
     *out = c;
     return EVPLP_OK;
 }
@@ -455,7 +448,7 @@ int evplp_download_bvh(evplp_handle c, uint64_t* mortonCodes, uint32_t* sortedPr
     const size_t n = c->numPrims, ni = n > 1 ? n - 1 : 0;
     if (mortonCodes && n) CU(cudaMemcpyAsync(mortonCodes, c->codesSorted.p, 8 * n, cudaMemcpyDeviceToHost, c->stream));
     if (sortedPrimIds && n) CU(cudaMemcpyAsync(sortedPrimIds, c->primIdsSorted.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
-    const bool haveTopo = (int)n > evplp::g_bvhLeafMax;  // tiny scenes skip the radix tree
+    const bool haveTopo = (int)n > c->opt.bvhLeafMax;  // tiny scenes skip the radix tree
     if (ni && !haveTopo && (left || right || parent || nodeBounds))
         return fail(EVPLP_ERR_INVALID, "evplp_download_bvh: scenes with <= BVH_LEAF_MAX triangles have no radix tree");
     if (left && ni) CU(cudaMemcpyAsync(left, c->left.p, 4 * ni, cudaMemcpyDeviceToHost, c->stream));
@@ -623,23 +616,35 @@ int evplp_event_elapsed_ms(evplp_handle c, int slotA, int slotB, float* ms) {
 }
 
 int evplp_set_option(evplp_handle c, const char* name, int value) {
-    (void)c;  // options are process-wide; the handle may be NULL (e.g. bvh_leaf_max must be set before evplp_build_bvh)
     NEED(name != nullptr, "evplp_set_option: NULL name");
-    if (strcmp(name, "gather_chunks") == 0) { evplp::g_gatherChunks = value; return EVPLP_OK; }
-    if (strcmp(name, "gather_band_stride") == 0) { NEED(value >= 0, "gather_band_stride must be >= 0"); evplp::g_bandStride = value; return EVPLP_OK; }
-    if (strcmp(name, "gather_band_offset") == 0) { NEED(value >= 0, "gather_band_offset must be >= 0"); evplp::g_bandOffset = value; return EVPLP_OK; }
-    if (strcmp(name, "gather_min_blocks") == 0) { evplp::g_gatherMinBlocks = value; return EVPLP_OK; }
-    if (strcmp(name, "bvh_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "bvh_leaf_max must be 1..8"); evplp::g_bvhLeafMax = value; return EVPLP_OK; }
-    if (strcmp(name, "shaft_leaf_max") == 0) { NEED(value >= 1 && value <= 8, "shaft_leaf_max must be 1..8"); evplp::g_shaftLeafMax = value; return EVPLP_OK; }
-    if (strcmp(name, "shaft_max_candidates") == 0) { evplp::g_shaftCandMax = value; return EVPLP_OK; }
-    if (strcmp(name, "shaft_streak") == 0) { evplp::g_shaftStreak = value; return EVPLP_OK; }
-    if (strcmp(name, "shaft_skip") == 0) { evplp::g_shaftSkip = value; return EVPLP_OK; }
-    if (strcmp(name, "gather_lpt") == 0) { evplp::g_gatherLpt = value != 0; return EVPLP_OK; }
-    if (strcmp(name, "gather_persistent") == 0) { evplp::g_gatherPersistent = value != 0; return EVPLP_OK; }
-    if (strcmp(name, "gather_mode") == 0) { evplp::g_gatherMode = value; return EVPLP_OK; }
-    if (strcmp(name, "splat_group") == 0) { evplp::g_splatGroup = value; return EVPLP_OK; }
-    if (strcmp(name, "splat_mode") == 0) { evplp::g_splatMode = value; return EVPLP_OK; }
-    if (strcmp(name, "splat_max_entries") == 0) { evplp::g_splatMaxEntries = value; return EVPLP_OK; }
+    // c == NULL: the defaults a handle created AFTERWARDS starts from; otherwise only this handle
+    std::unique_lock<std::mutex> lock(g_defaultsMutex, std::defer_lock);
+    if (!c) lock.lock();
+    evplp::Options& o = c ? c->opt : g_defaultOptions;
+    struct Knob { const char* name; int* slot; int lo, hi; };
+    int splatMaxEntries = 0;
+    const Knob knobs[] = {
+        {"gather_chunks", &o.gatherChunks, 0, 4096},
+        {"gather_band_stride", &o.bandStride, 0, 65536}, {"gather_band_offset", &o.bandOffset, 0, 65535},
+        {"gather_min_blocks", &o.gatherMinBlocks, 0, 5},
+        {"gather_mode", &o.gatherMode, 0, 2}, {"gather_algo", &o.gatherAlgo, 0, 1}, {"gather_cluster_size", &o.clusterSize, 1, 32},
+        {"shaft_max_candidates", &o.shaftCandMax, 1, evplp::SHAFT_CAND}, {"shaft_streak", &o.shaftStreak, 1, 1 << 20},
+        {"shaft_skip", &o.shaftSkip, 0, 1 << 20},
+        {"gather_lpt", &o.gatherLpt, 0, 1}, {"gather_persistent", &o.gatherPersistent, 0, 1},
+        {"splat_group", &o.splatGroup, 0, 32}, {"splat_mode", &o.splatMode, 0, 1}, {"splat_max_entries", &splatMaxEntries, 0, 0x7fffffff},
+        {"bvh_leaf_max", &o.bvhLeafMax, 1, 8}, {"shaft_leaf_max", &o.shaftLeafMax, 1, 8},
+    };
+    for (const Knob& k : knobs) {
+        if (strcmp(name, k.name) != 0) continue;
+        if (value < k.lo || value > k.hi)
+            return fail(EVPLP_ERR_INVALID, std::string("evplp_set_option: ") + name + " must be in [" + std::to_string(k.lo) + ", " + std::to_string(k.hi) + "]");
+        if (k.slot == &o.splatGroup && !(value == 0 || value == 1 || value == 8 || value == 32))
+            return fail(EVPLP_ERR_INVALID, "evplp_set_option: splat_group must be 0, 1, 8 or 32");
+        *k.slot = value;
+        if (k.slot == &splatMaxEntries) o.splatMaxEntries = value;
+        if (c && (k.slot == &o.bandStride || k.slot == &o.bandOffset)) c->gatherCostValid = false;
+        return EVPLP_OK;
+    }
     return fail(EVPLP_ERR_INVALID, std::string("evplp_set_option: unknown option ") + name);
 }
 

@@ -35,9 +35,25 @@ struct DevStats {
     int pad;
 };
 
+// Tuning knobs (evplp_set_option).  Every handle owns a copy; the process-wide defaults are only what a handle starts from.
+struct Options {
+    int gatherChunks = 0;        // 0 = automatic; 1 = one thread sums a pixel's VPLs in record order (bit-exact test mode)
+    int bandStride = 0, bandOffset = 0;   // image partition of the gather (multi-GPU): this handle owns tiles t = offset (mod stride)
+    int gatherMinBlocks = 0;     // 0 = per-kernel default
+    int gatherMode = 1;          // 1 = shaft traversal of the 32-wide hierarchy, 0 = per-ray packet traversal, 2 = shaft in VSL too
+    int gatherAlgo = 1;          // 1 = VPL-cluster gather (tolerance mode, default), 0 = per-VPL exact-order gather
+    int clusterSize = 16;        // VPLs per cluster of the cluster gather
+    int shaftCandMax = 128, shaftStreak = 3, shaftSkip = 256;
+    int gatherLpt = 1, gatherPersistent = 1;
+    int splatGroup = 0, splatMode = 0;
+    long long splatMaxEntries = 256ll * 1024 * 1024;
+    int bvhLeafMax = BVH_LEAF_MAX, shaftLeafMax = 2;
+};
+
 }  // namespace evplp
 
 struct EvplpContext {
+    evplp::Options opt;
     int device = 0;
     int W = 0, H = 0;
     cudaStream_t stream = nullptr;

@@ -1084,18 +1084,6 @@ cudaError_t launch_light_trace(EvplpContext* c, uint32_t rngSeed, uint32_t first
     return cudaGetLastError();
 }
 
-extern int g_gatherChunks;     // capi.cu (0 = automatic)
-extern int g_bandStride, g_bandOffset;  // capi.cu: 16-row band interleave of the gather (multi-GPU image partition)
-extern int g_splatGroup;       // capi.cu: lanes per photon in the scatter splat (0 = 32; 1 / 8 / 32)
-extern int g_splatMode;        // capi.cu: 0 = tiled splat (default), 1 = scatter splat
-extern int g_splatMaxEntries;  // capi.cu: tiled splat falls back to scatter above this many (photon, tile) entries
-extern int g_shaftCandMax;     // capi.cu
-extern int g_gatherPersistent;
-extern int g_gatherLpt;
-extern int g_shaftStreak, g_shaftSkip;
-extern int g_gatherMode;       // capi.cu: 0 = per-ray packet traversal, 1 = shaft traversal of the 32-wide hierarchy
-extern int g_gatherMinBlocks;  // capi.cu: resident blocks per SM the gather kernel is compiled for (2, 3 or 4)
-
 static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
     const EvplpParams& P = c->params;
     GatherParams g;
@@ -1107,10 +1095,10 @@ static GatherParams gather_params(EvplpContext* c, EvplpTile t) {
     g.numChunks = 1;
     g.vslRadius = P.vslRadius; g.vslInvPiRadius2 = P.vslInvPiRadius2;
     g.numLightPaths = P.numLightPaths; g.numVplLightPaths = P.numVplLightPaths; g.B1 = P.numPhotonsPerLightPath;
-    g.shaftMode = g_gatherMode == 2 ? 1 : 0;  // VSL gather: sampling-bound, the shaft brings nothing there (measured); opt-in with gather_mode = 2
-    g.shaftCandMax = g_shaftCandMax < 1 ? 1 : (g_shaftCandMax > SHAFT_CAND ? SHAFT_CAND : g_shaftCandMax);
-    g.bandStride = g_bandStride > 0 ? g_bandStride : 1;
-    g.bandOffset = g_bandStride > 0 ? g_bandOffset : 0;
+    g.shaftMode = c->opt.gatherMode == 2 ? 1 : 0;  // VSL gather: sampling-bound, the shaft brings nothing there (measured); opt-in with gather_mode = 2
+    g.shaftCandMax = c->opt.shaftCandMax < 1 ? 1 : (c->opt.shaftCandMax > SHAFT_CAND ? SHAFT_CAND : c->opt.shaftCandMax);
+    g.bandStride = c->opt.bandStride > 0 ? c->opt.bandStride : 1;
+    g.bandOffset = c->opt.bandStride > 0 ? c->opt.bandOffset : 0;
     return g;
 }
 
@@ -1155,8 +1143,8 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     }
     // split the VPL list over gridDim.z when the tile alone cannot fill the GPU
     unsigned chunks = 1;
-    if (g_gatherChunks > 0) {
-        chunks = (unsigned)g_gatherChunks;
+    if (c->opt.gatherChunks > 0) {
+        chunks = (unsigned)c->opt.gatherChunks;
     } else {
         const unsigned blocks = grid.x * grid.y;
         const unsigned want = 148u * 3u * 6u;  // ~6 waves of resident blocks, so the tail wave stays short
@@ -1172,9 +1160,9 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         c->launches++;
     }
     g.vgx = grid.x; g.vgy = grid.y; g.vgz = grid.z;
-    g.persistent = g_gatherPersistent;
-    g.shaftStreak = g_shaftStreak > 0 ? g_shaftStreak : 1;
-    g.shaftSkip = g_shaftSkip;
+    g.persistent = c->opt.gatherPersistent;
+    g.shaftStreak = c->opt.shaftStreak > 0 ? c->opt.shaftStreak : 1;
+    g.shaftSkip = c->opt.shaftSkip;
     uint32_t* tileCounter = c->counters.p + 2;  // (slots 0-2 belong to the BVH build, which is over by now)
     dim3 lgrid = grid;
     const uint32_t* tileOrder = nullptr;
@@ -1182,7 +1170,7 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     if (g.persistent) {
         e = cudaMemsetAsync(tileCounter, 0, sizeof(uint32_t), c->stream);
         if (e != cudaSuccess) return e;
-        if (g_gatherLpt) {
+        if (c->opt.gatherLpt) {
             // longest-processing-time-first: order the tiles by the cycles they took in the previous launch of this grid
             const uint32_t vTotal = grid.x * grid.y * grid.z * GATHER_WARPS;
             const uint64_t sig[4] = {((uint64_t)grid.x << 40) | ((uint64_t)grid.y << 20) | grid.z,
@@ -1217,8 +1205,8 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         lgrid = dim3(blocks < resident ? blocks : resident, 1, 1);
     }
     c->stageBegin(ST_GATHER);
-    if (g_gatherMode >= 1) {
-        const int mb = g_gatherMinBlocks ? g_gatherMinBlocks : 4;  // measured: 64 registers / 4 blocks per SM wins by 5 % here
+    if (c->opt.gatherMode >= 1) {
+        const int mb = c->opt.gatherMinBlocks ? c->opt.gatherMinBlocks : 4;  // measured: 64 registers / 4 blocks per SM wins by 5 % here
         if (mb == 2)
             gather_vpl_kernel<2, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost);
         else if (mb == 5)
@@ -1228,7 +1216,7 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         else
             gather_vpl_kernel<3, true><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost);
     } else {
-        switch (g_gatherMinBlocks) {
+        switch (c->opt.gatherMinBlocks) {
             case 2: gather_vpl_kernel<2, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost); break;
             case 4: gather_vpl_kernel<4, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost); break;
             default: gather_vpl_kernel<3, false><<<lgrid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->gbuf.p, c->records.p, c->vplList.p, devCount, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost); break;
@@ -1271,7 +1259,7 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
     sp.camFwd = v3p(P.camForward); sp.camRight = v3p(P.camRight); sp.camUp = v3p(P.camUp);
     sp.tanX = P.tanHalfFovX; sp.tanY = P.tanHalfFovY; sp.jx = P.jitter[0]; sp.jy = P.jitter[1]; sp.nearD = P.nearDist;
     sp.x0 = t.x0; sp.y0 = t.y0; sp.x1 = t.x1; sp.y1 = t.y1; sp.W = c->W; sp.H = c->H;
-    if (g_splatMode != 1) {
+    if (c->opt.splatMode != 1) {
         // ---- tiled path: bin -> scan -> fill -> per-tile accumulation
         TileGrid tg;
         tg.tx0 = t.x0 / SPLAT_TILE; tg.ty0 = t.y0 / SPLAT_TILE;
@@ -1298,7 +1286,7 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
         e = cudaMemcpyAsync(&maxPerTile, summary, 4, cudaMemcpyDeviceToHost, c->stream); if (e != cudaSuccess) return e;
         e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) return e;
         if (totalEntries == 0) { c->stageEnd(ST_SPLAT); return cudaSuccess; }
-        if ((uint64_t)totalEntries <= (uint64_t)g_splatMaxEntries) {
+        if ((uint64_t)totalEntries <= (uint64_t)c->opt.splatMaxEntries) {
             e = c->tileList.reserve(totalEntries); if (e != cudaSuccess) return e;
             splat_fill_kernel<<<pb, 256, 0, c->stream>>>(sp, tg, c->splatPrep.p, devCount, c->tileOffset.p, c->tileCursor.p, c->tileList.p);
             const unsigned chunks = (maxPerTile + SPLAT_CHUNK - 1) / SPLAT_CHUNK;
@@ -1311,7 +1299,7 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
         }
         // footprints so large that the tile lists would not fit: fall through to the scatter kernel
     }
-    const int G = g_splatGroup > 0 ? g_splatGroup : 32;
+    const int G = c->opt.splatGroup > 0 ? c->opt.splatGroup : 32;
     const uint64_t threadsWanted = (uint64_t)count * (uint64_t)G;
     uint64_t blocks = (threadsWanted + 255) / 256;
     const uint64_t maxBlocks = 148ull * 8ull * 8ull;

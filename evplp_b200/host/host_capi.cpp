@@ -1,9 +1,16 @@
 // host_capi.cpp -- C entry points over the C++ host classes, for ctypes callers (tests, bench.py).
 // No compute happens here: scene generation / loading is host data preparation and every
 // render call goes through libevplp_b200.so.
+// Compiled twice: into libevplp_host.so (everything; links libevplp_b200.so) and, with -DEVPLP_SCENE_ONLY, into
+// libevplp_scene.so (scene generation / loading / descriptors only; links NOTHING of the product, so that the CPU
+// reference arm of bench.py can build its inputs without mapping the product library).
 #include <cstring>
+#ifndef EVPLP_SCENE_ONLY
 #include "rtcomphoton.h"
 #include "rtpt2.h"
+#else
+#include "rtcommon.h"
+#endif
 #include "scenegen.h"
 
 using namespace evplp_host;
@@ -16,10 +23,12 @@ struct HostScene {
     std::vector<EvplpMaterialDesc> mt;
 };
 
+#ifndef EVPLP_SCENE_ONLY
 struct HostTechnique {
     std::unique_ptr<RtComPhoton> tech;
     shared_ptr<RtScene> scene;
 };
+#endif
 
 #define GUARD(...) try { __VA_ARGS__ } catch (const std::exception& e) { g_hostErr = e.what(); return -1; }
 
@@ -86,6 +95,7 @@ int evplp_host_scene_info(void* s, float scalars[3], float camera[14]) {
     )
 }
 
+#ifndef EVPLP_SCENE_ONLY
 // RtComPhoton / RtLvcComPhoton over a scene; `techniqueJson` is the text of the "photonfam" object.
 // partitionMode: 0 = iterations round-robin over the ranks, 1 = image bands + light-path ranges (RtComPhoton::EPartition)
 void* evplp_host_technique_create(void* s, const char* techniqueJson, int resX, int resY, int device, int lvc, int rank, int worldSize,
@@ -238,6 +248,8 @@ int evplp_host_config_check(void* s, const char* jsonPath, double out[80]) {
         }
         return 0;)
 }
+
+#endif  // !EVPLP_SCENE_ONLY
 
 // texture decoding taps: a JPEG byte stream -> top-down RGB8 (what stbi_load(path, .., 3) returns without the
 // flip), and a texture file -> the RGBA32F texels RtTexture hands to evplp_upload_scene

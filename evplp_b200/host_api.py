@@ -12,8 +12,36 @@ from .scene import Material, Mesh, Scene
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libevplp_host.so")
+SCENE_LIB_PATH = os.path.join(_HERE, "lib", "libevplp_scene.so")
 _P = C.c_void_p
 _lib = None
+_scene_lib = None
+
+
+def _bind_scene_symbols(lib):
+    lib.evplp_host_last_error.restype = C.c_char_p
+    lib.evplp_host_export_scene.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    lib.evplp_host_generate_scene.restype = _P
+    lib.evplp_host_generate_scene.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_float]
+    lib.evplp_host_load_scene.restype = _P
+    lib.evplp_host_load_scene.argtypes = [C.c_char_p]
+    lib.evplp_host_scene_destroy.argtypes = [_P]
+    lib.evplp_host_scene_descriptors.argtypes = [_P, C.POINTER(C.POINTER(capi.MeshDesc)), C.POINTER(C.c_int32),
+                                                 C.POINTER(C.POINTER(capi.MaterialDesc)), C.POINTER(C.c_int32),
+                                                 C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.evplp_host_scene_info.argtypes = [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+
+
+def load_scene_library():
+    """libevplp_scene.so: scene generation / loading only, linked against nothing of the product (the CPU reference arm
+    of bench.py builds its inputs with it, so that it never maps libevplp_b200.so)."""
+    global _scene_lib
+    if _scene_lib is None:
+        if not os.path.exists(SCENE_LIB_PATH):
+            raise RuntimeError(f"{SCENE_LIB_PATH} not found: run __graft_entry__.build()")
+        _scene_lib = C.CDLL(SCENE_LIB_PATH)
+        _bind_scene_symbols(_scene_lib)
+    return _scene_lib
 
 
 def load_host_library():
@@ -76,8 +104,8 @@ def _err(lib, what):
 class HostScene:
     """An RtScene living in the C++ host library."""
 
-    def __init__(self, handle):
-        self.lib = load_host_library()
+    def __init__(self, handle, lib=None):
+        self.lib = lib or load_host_library()
         self.h = handle
         s = (C.c_float * 3)()
         cam = (C.c_float * 14)()
@@ -91,12 +119,12 @@ class HostScene:
         self.tan_x, self.tan_y = c[12], c[13]
 
     @classmethod
-    def generate(cls, name, seed=1, detail=8, aspect=16 / 9):
-        lib = load_host_library()
+    def generate(cls, name, seed=1, detail=8, aspect=16 / 9, scene_only=False):
+        lib = load_scene_library() if scene_only else load_host_library()
         h = lib.evplp_host_generate_scene(name.encode(), seed, detail, aspect)
         if not h:
             _err(lib, "evplp_host_generate_scene")
-        return cls(h)
+        return cls(h, lib)
 
     @classmethod
     def load(cls, json_path):

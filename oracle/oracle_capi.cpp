@@ -1,7 +1,7 @@
 // oracle_capi.cpp -- TEST INFRASTRUCTURE (CPU oracle): C entry points for ctypes.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load liboracle.so.  The product (libevplp_b200.so, evplp_b200/) never does.
-// Parity status: PARITY UNPINNED by the reference (no tests there); see oracle_math.h.
+// Parity status: pinned by the reference's own device code for the CUDA programs, see oracle_math.h.
 #include <omp.h>
 #include <stdio.h>
 #include <string.h>
@@ -80,6 +80,8 @@ void orc_light_cdf(void* h, float* out) {
     memcpy(out, s->lightCdf.data(), s->lightCdf.size() * 4);
 }
 int32_t orc_num_threads(void) { return omp_get_max_threads(); }
+// torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; callers that time the oracle set the count explicitly
+void orc_set_threads(int32_t n) { if (n > 0) omp_set_num_threads(n); }
 
 // RtScene::totalArea (rtcommon.h:759-768) and findBoundingSphereRadius (rtcommon.h:805-814);
 // meshStart[numMeshes+1] gives the primitive range of each mesh (sequential f32 sums per mesh).
@@ -354,6 +356,30 @@ void orc_resolve(void* h, int32_t W, int32_t H, const int64_t* vpl, const int64_
             res[c] = doGamma ? powf(sum, 1.0f / 2.2f) : sum;
         }
         outRGB[i * 3] = res[0]; outRGB[i * 3 + 1] = res[1]; outRGB[i * 3 + 2] = res[2];
+    }
+}
+
+// BRDF library taps, item by item the same calls as oracle/ref_device.cu:k_brdf makes into the reference's own
+// rtmaterial.cuh / rtmath.cuh / lighttracing.cu functions: in = 16 floats per item, out = 8 floats per item.
+void orc_brdf(int32_t op, const float* in16, uint32_t n, float* out8) {
+    for (uint32_t i = 0; i < n; i++) {
+        const float* q = in16 + (size_t)i * 16;
+        float* o = out8 + (size_t)i * 8;
+        const F3 a = mk3(q[0], q[1], q[2]), b = mk3(q[3], q[4], q[5]), c = mk3(q[6], q[7], q[8]), refl = mk3(q[9], q[10], q[11]);
+        const float e = q[12];
+        for (int k = 0; k < 8; k++) o[k] = 0.f;
+        CurandState st;
+        curand_init((unsigned)q[13], (unsigned)q[14], 0, &st);
+        F3 dir = mk3(0.f, 0.f, 0.f);
+        float pdf = 0.f;
+        switch (op) {
+            case 0: { F3 r = LambertSample(&dir, &pdf, a, b, refl, &st); setv(o, dir); o[3] = pdf; setv(o + 4, r); o[7] = curand_uniform(&st); break; }
+            case 1: { F3 r = PhongSample(&dir, &pdf, a, b, refl, e, &st); setv(o, dir); o[3] = pdf; setv(o + 4, r); o[7] = curand_uniform(&st); break; }
+            case 2: o[0] = LambertPdfA(a, b, c); o[1] = LambertPdfW(a, c); o[2] = pt::GeometryTerm(a, b, c); break;
+            case 3: o[0] = PhongPdfA(a, b, c, refl, mk3(q[15], q[15], q[15]), e); o[1] = PhongPdfW(a, c, refl, mk3(q[15], q[15], q[15]), e); break;
+            case 4: { o[0] = PhongEvalF(a, b, c, e); F3 r = pt::PhongEval(a, b, c, refl, e); setv(o + 1, r); break; }
+            case 5: { float be, ga; SquareToBarycentric(&be, &ga, q[0], q[1]); o[0] = be; o[1] = ga; F3 sa = SquareToSolidAngle(q[0], q[1], q[2]); setv(o + 2, sa); o[5] = russianProb(b); break; }
+        }
     }
 }
 

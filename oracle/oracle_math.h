@@ -7,9 +7,14 @@
 // reference: rtmaterial.cuh:58-60,81,106,122,136-137; lighttracing.cu:115-116,236,292;
 // triangleintersect.cu:27.
 //
-// Parity status: PARITY UNPINNED by the reference (it has no tests / golden vectors,
-// SURVEY.md §4); the oracle is pinned instead against cuRAND itself (device curand_init),
-// the mt19937 standard vector, glibc libm (accuracy of detmath) and analytic identities.
+// Parity status: PINNED BY THE REFERENCE'S OWN DEVICE CODE for the CUDA programs -- lighttracing.cu, pathtracing.cu,
+// triangleintersect.cu, rtmaterial.cuh, rtmath.cuh, rtlightsource.cuh are compiled UNMODIFIED from /root/reference
+// (oracle/ref_device*.cu + oracle/ref_shim/, `make -C oracle refdevice` -> oracle/_ref/libref_device*.so), run on a B200,
+// and this oracle must equal what they return: flags / counts / RNG consumption exactly, floats to 1e-5
+// (tests/ref_cases.py; live: tests/test_gpu_reference.py; on CPU from the stored outputs: tests/test_ref_goldens.py).
+// Still UNPINNED (the reference holds no runnable code or vectors for them): the GLSL stages (photon splat, G-buffer,
+// final composite), the host-side schedule and the LVC splatColor loop (lvclighttracing.cu:348-387 uses an MSVC-only cast).
+// Also pinned: XORWOW against cuRAND itself (device curand_init), the mt19937 standard vector, detmath against libm.
 //
 // Compile with -ffp-contract=off: every expression below must round exactly as written.
 #pragma once

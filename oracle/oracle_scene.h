@@ -1,6 +1,6 @@
 // oracle_scene.h -- TEST INFRASTRUCTURE (CPU oracle): RNG streams, scene arrays,
 // software texture fetch, ray/triangle test and a plain median-split BVH.
-// Parity status: PARITY UNPINNED by the reference (no tests there); see oracle_math.h.
+// Parity status: pinned by the reference's own device code for the CUDA programs, see oracle_math.h.
 #pragma once
 #include <algorithm>
 #include <vector>

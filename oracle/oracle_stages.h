@@ -9,7 +9,7 @@
 //   LVC splatColor ....... realtimetechniques/lvclighttracing.cu:348-387
 //   photon splat ......... shaders/photonsplatinstanced.{vert,geom,frag}
 //   G-buffer ............. shaders/deferred.{geom,frag} (ray-cast definition)
-// Parity status: PARITY UNPINNED by the reference (it ships no tests); see oracle_math.h.
+// Parity status: pinned by the reference's own device code for the CUDA programs, see oracle_math.h.
 #pragma once
 #include "oracle_scene.h"
 

@@ -40,6 +40,8 @@ def load():
     lib.orc_light_area.argtypes = [_P]
     lib.orc_light_cdf.argtypes = [_P, _P]
     lib.orc_num_threads.restype = C.c_int32
+    lib.orc_set_threads.argtypes = [C.c_int32]
+    lib.orc_brdf.argtypes = [C.c_int32, _P, C.c_uint32, _P]
     lib.orc_total_area.restype = C.c_float
     lib.orc_total_area.argtypes = [_P, _P, C.c_int32]
     lib.orc_uniforms.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, _P]
