@@ -352,6 +352,17 @@ def run_gpu(args):
         if dbg[0]:
             line["shaft_gather"] = {"steps": int(dbg[0]), "fallback_frac": dbg[1] / dbg[0], "nodes_per_step": dbg[2] / dbg[0],
                                     "candidate_leaves_per_step": dbg[3] / max(dbg[0] - dbg[1], 1), "nodes4": int(dbg[4]), "nodes32": int(dbg[5])}
+            hist = (C.c_uint64 * 16)()
+            ck(lib.evplp_debug_cluster_hist(h, hist), "debug_cluster_hist")
+            if dbg[6]:
+                line["cluster_gather"] = {"descents_per_step": dbg[6] / dbg[0], "candidate_batches_per_descent": dbg[7] / dbg[6],
+                                          "candidates_per_descent": dbg[3] / dbg[6], "packet_steps_frac": dbg[1] / dbg[0]}
+                if os.environ.get("EVPLP_LIB"):   # tuning build (-DEVPLP_GATHER_PROF): warp-cycles per region of the item loop
+                    line["cluster_gather"]["prof_cycles_stage_clusterdescent_sharedtests_vpldescent_vpltests_packet_shading_setup"] = [
+                        int(hist[k]) for k in (1, 2, 3, 4, 5, 6, 7, 8)]
+                elif any(hist):   # tuning build (-DEVPLP_GATHER_HIST)
+                    line["cluster_gather"].update({"candidates_per_descent_hist_0_8_32_64_128_512_more": [int(hist[k]) for k in range(7)],
+                                                   "cluster_tile_pairs": int(hist[8]), "lit_pairs": int(hist[9]), "lit_vpls": int(hist[10])})
         if world == 1 and not args.no_cpu:
             pps, csec, cores, desc = cpu_sample(1, 0)
             line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc}

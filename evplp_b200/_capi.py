@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libevplp_b200.so")
+LIB_PATH = os.environ.get("EVPLP_LIB") or os.path.join(_HERE, "lib", "libevplp_b200.so")   # EVPLP_LIB: a tuning build of the same library
 
 EVPLP_OK = 0
 FLAG_USABLE_VPL, FLAG_USABLE_PHOTON, FLAG_LAMBERT_ONLY, FLAG_PHONG_ONLY = 1, 2, 4, 8
@@ -103,6 +103,8 @@ SYMBOLS = {
     "evplp_path_trace": (C.c_int, [_P, C.POINTER(Tile), C.c_uint32]),
     "evplp_photon_splat": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.POINTER(Tile)]),
     "evplp_light_pass": (C.c_int, [_P]),
+    "evplp_add_iterations": (C.c_int, [_P, C.c_int64]),
+    "evplp_iterations": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "evplp_reduce": (C.c_int, [_P, _P]),
     "evplp_accum_layer": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "evplp_resolve": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
@@ -123,6 +125,7 @@ SYMBOLS = {
     "evplp_synchronize": (C.c_int, [_P]),
     "evplp_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "evplp_debug_counters": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "evplp_debug_cluster_hist": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "evplp_event_record": (C.c_int, [_P, C.c_int]),
     "evplp_event_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "evplp_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),

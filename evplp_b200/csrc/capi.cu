@@ -86,6 +86,8 @@ int evplp_create(int device, int width, int height, evplp_handle* out) {
     CU(c->accVpl.reserve(3 * n_px));
     CU(c->accPhoton.reserve(3 * n_px));
     CU(c->accLight.reserve(n_px));
+    CU(c->accCount.reserve(2));
+    CU(cudaMemsetAsync(c->accCount.p, 0, 2 * sizeof(long long), c->stream));
     CU(c->resolveOut.reserve(3 * n_px));
     CU(c->devStats.reserve(1));
     CU(c->skipMatrix.reserve(kSkipMatrixWords));
@@ -116,8 +118,8 @@ int evplp_destroy(evplp_handle c) {
     c->refitFlags.release(); c->nodes.release(); c->shaftNodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
     c->gatherCost.release(); c->gatherCostSorted.release(); c->gatherIota.release(); c->gatherOrder.release();
     c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->records.release();
-    c->vplList.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
-    c->accPhoton.release(); c->accLight.release(); c->resolveOut.release(); c->devStats.release();
+    c->vplList.release(); c->vplKeys.release(); c->vplKeysSorted.release(); c->vplVals.release(); c->vplOrder.release(); c->vplPrepared.release(); c->clusterBox.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
+    c->accPhoton.release(); c->accLight.release(); c->accCount.release(); c->resolveOut.release(); c->devStats.release();
     if (c->resolvePinned) cudaFreeHost(c->resolvePinned);
     for (int s = 0; s < ST_COUNT; s++) { cudaEventDestroy(c->stageA[s]); cudaEventDestroy(c->stageB[s]); }
     for (int s = 0; s < 4; s++) cudaEventDestroy(c->userEv[s]);
@@ -204,6 +206,11 @@ int evplp_upload_scene(evplp_handle c, const EvplpMeshDesc* meshes, int32_t numM
     CU(cudaStreamSynchronize(c->stream));
     c->numPrims = (int)numPrims; c->numMats = numMaterials;
     c->lightFirst = lightFirst; c->lightCount = lightCount; c->lightArea = sumArea;
+    for (int k = 0; k < 3; k++) { c->lightBoxMin[k] = 3.0e38f; c->lightBoxMax[k] = -3.0e38f; }
+    for (size_t v = 3 * (size_t)lightFirst; v < 3 * (size_t)(lightFirst + lightCount); v++) {
+        const float q[3] = {verts[v].x, verts[v].y, verts[v].z};
+        for (int k = 0; k < 3; k++) { c->lightBoxMin[k] = fminf(c->lightBoxMin[k], q[k]); c->lightBoxMax[k] = fmaxf(c->lightBoxMax[k], q[k]); }
+    }
     memcpy(c->lightIntensity, lightIntensityPrecomputed, 16);
     memcpy(c->lightDisplay, lightIntensityDisplay, 16);
     c->sceneLoaded = true;
@@ -252,6 +259,24 @@ int evplp_clear_accum(evplp_handle c) {
     CU(cudaMemsetAsync(c->accVpl.p, 0, sizeof(long long) * 3 * n, c->stream));
     CU(cudaMemsetAsync(c->accPhoton.p, 0, sizeof(long long) * 3 * n, c->stream));
     CU(cudaMemsetAsync(c->accLight.p, 0, sizeof(uint32_t) * n, c->stream));
+    CU(cudaMemsetAsync(c->accCount.p, 0, 2 * sizeof(long long), c->stream));
+    return EVPLP_OK;
+}
+
+int evplp_add_iterations(evplp_handle c, int64_t n) {
+    NEED(c != nullptr, "evplp_add_iterations: NULL handle");
+    CU(cudaSetDevice(c->device));
+    CU(launch_add_count(c, (long long)n));
+    return EVPLP_OK;
+}
+
+int evplp_iterations(evplp_handle c, int64_t* n) {
+    NEED(c != nullptr && n != nullptr, "evplp_iterations: NULL argument");
+    CU(cudaSetDevice(c->device));
+    long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->accCount.p, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *n = (int64_t)v;
     return EVPLP_OK;
 }
 
@@ -331,7 +356,7 @@ int evplp_photon_splat(evplp_handle c, uint64_t firstRecord, uint64_t numRecords
 
 int evplp_light_pass(evplp_handle c) {
     NEED(c != nullptr, "evplp_light_pass: NULL handle");
-    NEED(c->gbufValid, "evplp_light_pass: needs a G-buffer first");
+    NEED(c->bvhBuilt && c->paramsSet, "evplp_light_pass: needs evplp_build_bvh and evplp_set_params first");
     CU(cudaSetDevice(c->device));
     CU(launch_light_pass(c));
     return EVPLP_OK;
@@ -361,6 +386,7 @@ int evplp_reduce(evplp_handle c, void* ncclComm) {
     int r = allReduce(c->accVpl.p, c->accVpl.p, 3 * n, ncclInt64, ncclSum, ncclComm, c->stream);
     if (r == 0) r = allReduce(c->accPhoton.p, c->accPhoton.p, 3 * n, ncclInt64, ncclSum, ncclComm, c->stream);
     if (r == 0) r = allReduce(c->accLight.p, c->accLight.p, n, ncclUint32, ncclSum, ncclComm, c->stream);
+    if (r == 0) r = allReduce(c->accCount.p, c->accCount.p, 1, ncclInt64, ncclSum, ncclComm, c->stream);
     if (r != 0) return fail(EVPLP_ERR_NCCL, "evplp_reduce: ncclAllReduce failed with code " + std::to_string(r));
     return EVPLP_OK;
 }
@@ -372,7 +398,8 @@ int evplp_accum_layer(evplp_handle c, int layer, void** devPtr, uint64_t* numEle
         case 0: *devPtr = c->accVpl.p; *numElems = 3 * n; break;
         case 1: *devPtr = c->accPhoton.p; *numElems = 3 * n; break;
         case 2: *devPtr = c->accLight.p; *numElems = n; break;
-        default: return fail(EVPLP_ERR_INVALID, "evplp_accum_layer: layer must be 0, 1 or 2");
+        case 3: *devPtr = c->accCount.p; *numElems = 1; break;
+        default: return fail(EVPLP_ERR_INVALID, "evplp_accum_layer: layer must be 0, 1, 2 or 3");
     }
     return EVPLP_OK;
 }
@@ -596,7 +623,17 @@ int evplp_debug_counters(evplp_handle c, uint64_t out[8]) {
     CU(cudaMemcpyAsync(&ds, c->devStats.p, sizeof(ds), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     out[0] = ds.shaftSteps; out[1] = ds.shaftFallbacks; out[2] = ds.shaftNodeVisits; out[3] = ds.shaftCandLeaves;
-    out[4] = (uint64_t)c->numNodes; out[5] = (uint64_t)c->numShaftNodes; out[6] = 0; out[7] = 0;
+    out[4] = (uint64_t)c->numNodes; out[5] = (uint64_t)c->numShaftNodes; out[6] = ds.clusterDescents; out[7] = ds.clusterSplits;
+    return EVPLP_OK;
+}
+
+int evplp_debug_cluster_hist(evplp_handle c, uint64_t out[16]) {
+    NEED(c != nullptr && out != nullptr, "evplp_debug_cluster_hist: NULL argument");
+    CU(cudaSetDevice(c->device));
+    DevStats ds;
+    CU(cudaMemcpyAsync(&ds, c->devStats.p, sizeof(ds), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 16; k++) out[k] = ds.clusterHist[k];
     return EVPLP_OK;
 }
 
@@ -627,7 +664,7 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
         {"gather_chunks", &o.gatherChunks, 0, 4096},
         {"gather_band_stride", &o.bandStride, 0, 65536}, {"gather_band_offset", &o.bandOffset, 0, 65535},
         {"gather_min_blocks", &o.gatherMinBlocks, 0, 5},
-        {"gather_mode", &o.gatherMode, 0, 2}, {"gather_algo", &o.gatherAlgo, 0, 1}, {"gather_cluster_size", &o.clusterSize, 1, 32},
+        {"gather_mode", &o.gatherMode, 0, 2}, {"gather_algo", &o.gatherAlgo, 0, 2}, {"gather_cluster_size", &o.clusterSize, 1, 32},
         {"shaft_max_candidates", &o.shaftCandMax, 1, evplp::SHAFT_CAND}, {"shaft_streak", &o.shaftStreak, 1, 1 << 20},
         {"shaft_skip", &o.shaftSkip, 0, 1 << 20},
         {"gather_lpt", &o.gatherLpt, 0, 1}, {"gather_persistent", &o.gatherPersistent, 0, 1},

@@ -31,6 +31,8 @@ enum Stage { ST_BVH = 0, ST_GBUFFER, ST_LIGHT_TRACE, ST_GATHER, ST_SPLAT, ST_RES
 struct DevStats {
     unsigned long long shadowRays, splatPhotons, splatFragments, closestRays, gatherPairs;
     unsigned long long shaftSteps, shaftFallbacks, shaftNodeVisits, shaftCandLeaves;  // tuning counters of the shaft gather
+    unsigned long long clusterDescents, clusterSplits;                               // cluster gather: descents, overflow splits
+    unsigned long long clusterHist[16];   // cluster gather: candidates per descent (0, <=8, <=32, <=64, <=96, overflow by span), live clusters / VPLs
     int stackOverflow;
     int pad;
 };
@@ -104,6 +106,10 @@ struct EvplpContext {
     uint64_t numRecords = 0;                      // valid records of the last trace / upload
     uint32_t recordsFirstPath = 0;
     evplp::DevBuf<uint32_t> vplList;              // indices of usable VPL records (gather prefix)
+    // cluster gather: Morton keys / record indices of the usable VPLs, their sorted order, the prepared VPLs (6 float4 each)
+    // and the cluster boxes (2 float4 each)
+    evplp::DevBuf<uint32_t> vplKeys, vplKeysSorted, vplVals, vplOrder;
+    evplp::DevBuf<float4> vplPrepared, clusterBox;
     evplp::DevBuf<uint32_t> photonList;           // indices of usable photon records
     evplp::DevBuf<float4> splatPrep;              // per-photon constants of the fragment shader (5 float4 each)
     evplp::DevBuf<uint32_t> tileCount, tileOffset, tileCursor, tileList;  // photon bins of the tiled splat
@@ -114,6 +120,8 @@ struct EvplpContext {
 
     evplp::DevBuf<long long> accVpl, accPhoton;   // Q31.32, W*H*3
     evplp::DevBuf<uint32_t> accLight;             // W*H
+    evplp::DevBuf<long long> accCount;            // [0] iterations accumulated into the layers (reduced with them)
+    float lightBoxMin[3] = {0, 0, 0}, lightBoxMax[3] = {0, 0, 0};   // world bounds of the light mesh (light pass rectangle)
     evplp::DevBuf<float> resolveOut;              // W*H*3
     float* resolvePinned = nullptr;
 
@@ -131,6 +139,34 @@ struct EvplpContext {
 
 namespace evplp {
 
+constexpr int GATHER_BATCH = 16;    // VPL records staged per warp and shared-memory batch
+constexpr int GATHER_WARPS = 8;
+
+struct GatherParams {
+    V3 cameraPosition;
+    unsigned misMode;
+    float pdfMc, clampingValue;
+    float invNumVpl;  // 1 / (float)numVplLightPaths
+    unsigned doAccumulate;
+    int x0, y0, x1, y1;  // tile
+    int W, H;
+    unsigned numChunks;  // VPL list split over gridDim.z
+    float vslRadius, vslInvPiRadius2;
+    unsigned numLightPaths, numVplLightPaths, B1;
+    int shaftMode;               // 1 = shaft traversal (gather_mode option)
+    int shaftCandMax;            // shaft gather: candidate leaves beyond which a (warp, VPL) step falls back to the packet traversal
+    int bandStride, bandOffset;  // this launch owns the 16-row bands b = bandOffset (mod bandStride) of the tile (multi-GPU interleave)
+    // VPL gather: the launch's (16x16-pixel block, VPL chunk) grid.  With persistent != 0 the kernel is launched with one
+    // resident wave of blocks and every WARP draws the next 8x4-pixel tile of that grid from a global counter, so warps
+    // whose tile is cheap (culled by the cosine test, sky) go on to new work instead of idling until their block ends.
+    unsigned vgx, vgy, vgz;
+    int persistent;
+    int shaftStreak, shaftSkip;  // shaft gather: overflows in a row before, and number of, steps sent straight to the packet traversal
+};
+
+// gather_fast.cu: the VPL-cluster gather (tolerance mode); `count` = usable VPLs in c->vplList (already compacted)
+cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile tile, GatherParams g, uint32_t count);
+
 // bvh.cu
 cudaError_t build_bvh_device(EvplpContext* c, std::string* err);
 // stages.cu
@@ -140,12 +176,14 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile tile, int mode);
 cudaError_t launch_path_trace(EvplpContext* c, EvplpTile tile, uint32_t maxBounces);
 cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numRecords, EvplpTile tile);
 cudaError_t launch_light_pass(EvplpContext* c);
+cudaError_t launch_add_count(EvplpContext* c, long long n);
 cudaError_t launch_resolve(EvplpContext* c, float vplScale, float photonScale, float lightScale, int gamma);
 cudaError_t launch_trace_rays(EvplpContext* c, const float* devRays, uint64_t n, int anyHit, int32_t* devPrim, float* devT);
 cudaError_t launch_debug_uniforms(EvplpContext* c, uint32_t seed, uint32_t n, float* devOut);
 cudaError_t launch_debug_curand(EvplpContext* c, uint32_t seed, uint32_t subsequence, uint32_t n, float* devOut);
 cudaError_t launch_count_flags(EvplpContext* c, unsigned long long counts[2]);
 cudaError_t launch_debug_math(EvplpContext* c, int op, const float* x, const float* y, uint32_t n, float* out);
+cudaError_t launch_debug_fast_pow(EvplpContext* c, const float* x, const float* y, uint32_t n, float* out);  // gather_fast.cu
 // host_xorwow.cpp
 void xorwow_compose_skip(uint32_t subsequence, uint32_t* out800);
 

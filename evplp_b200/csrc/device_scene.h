@@ -95,16 +95,25 @@ __device__ __forceinline__ bool slab_test(const RaySlab& s, const WideNode& nd, 
     return tn <= tf;
 }
 
-// optix::intersect_triangle_branchless with the ray-independent terms precomputed.
+// optix::intersect_triangle_branchless with the ray-independent terms precomputed.  Every operation is an explicit
+// round-to-nearest intrinsic in the association order of vec.h, so the hit decision has the oracle's bits in ANY
+// translation unit -- also in gather_fast.cu, which is compiled with FMA contraction.
+__device__ __forceinline__ float dot_rn(V3 a, V3 b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ V3 cross_rn(V3 a, V3 b) {
+    return v3(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+              __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
 __device__ __forceinline__ bool tri_test(V3 org, V3 dir, float tmin, float tmax, V3 p0, V3 e0, V3 e1, V3 n,
                                          float* t, float* beta, float* gamma) {
-    const float inv = det_div(1.0f, dot(n, dir));
-    const V3 e2 = inv * (p0 - org);
-    const V3 i = cross(dir, e2);
-    *beta = dot(i, e1);
-    *gamma = dot(i, e0);
-    *t = dot(n, e2);
-    return (*t < tmax) & (*t > tmin) & (*beta >= 0.0f) & (*gamma >= 0.0f) & (*beta + *gamma <= 1.0f);
+    const float inv = __fdiv_rn(1.0f, dot_rn(n, dir));
+    const V3 e2 = v3(__fmul_rn(inv, __fsub_rn(p0.x, org.x)), __fmul_rn(inv, __fsub_rn(p0.y, org.y)), __fmul_rn(inv, __fsub_rn(p0.z, org.z)));
+    const V3 i = cross_rn(dir, e2);
+    *beta = dot_rn(i, e1);
+    *gamma = dot_rn(i, e0);
+    *t = dot_rn(n, e2);
+    return (*t < tmax) & (*t > tmin) & (*beta >= 0.0f) & (*gamma >= 0.0f) & (__fadd_rn(*beta, *gamma) <= 1.0f);
 }
 
 __device__ __forceinline__ V3 ld3(const float4& v) { return v3(v.x, v.y, v.z); }

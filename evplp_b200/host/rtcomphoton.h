@@ -151,6 +151,10 @@ public:
         mNumIterations = 0;
         check(evplp_clear_accum(mHandle), "evplp_clear_accum");
         const bool imageMode = mPartition == PartitionImage && mWorldSize > 1;
+        // cleareveryframe shows ONE frame; dealing iterations round-robin would leave a different "last frame" on every rank
+        // and the reduce would add them up.  A single frame is split over the ranks by image tiles / light-path ranges instead.
+        if (mFrameMode == ClearEveryFrame && mWorldSize > 1 && !imageMode)
+            throw std::runtime_error("frameMode cleareveryframe with several ranks needs the image partition (PartitionImage)");
         check(evplp_set_option(mHandle, "gather_band_stride", imageMode ? mWorldSize : 0), "evplp_set_option");
         check(evplp_set_option(mHandle, "gather_band_offset", imageMode ? mRank : 0), "evplp_set_option");
         mMasterWatch.reset();
@@ -267,6 +271,8 @@ public:
                 runStreamed((uint32_t)mNumIterations + mRngOffset);
             }
             if (mDoLightRender && (!imageMode || mRank == 0)) runLightProgram();
+            // one more iteration sits in the layers (image partition: every rank holds a share of it, rank 0 counts it)
+            if (!imageMode || mRank == 0) check(evplp_add_iterations(mHandle, 1), "evplp_add_iterations");
         }
         mNumIterations++;
         if (mNumIterations % 20 == 0 && mRank == 0) {
@@ -279,7 +285,10 @@ public:
             ProgressiveUpdate(mNumIterations, mAlphaProgressive, mClampingStart, mNumVplLightPaths, mNumLightPaths, mForceVsl,
                               &mPhotonRadius, &mClampingValue, &mPrecomptedPdfMc, &mVslRadius, &mVslInvPiRadius2);
         }
-        if (mTimelimitMs > 0 && mMasterWatch.timeMilliSec() >= mTimelimitMs) return false;
+        // rtcomphoton.h:1065 compares unconditionally (a non-positive limit ends the run after one iteration).  With several ranks
+        // each rank watches its own clock and may leave the loop at a different iteration; finish() normalises by the number
+        // of iterations that were actually accumulated (reduced with the layers), so the image stays correctly exposed.
+        if (mMasterWatch.timeMilliSec() >= mTimelimitMs) return false;
         return true;
     }
 
@@ -309,7 +318,7 @@ public:
             std::ofstream of(mStatFilename);
             of << result.dump(4);
         }
-        const float param = (mFrameMode == ClearEveryFrame) ? 1.0f : (1.0f / (float)(mNumIterations));
+        const float param = (mFrameMode == ClearEveryFrame) ? 1.0f : (1.0f / (float)accumulatedIterations());
         FloatImage lightSourceImage = FloatImage::FlipY(runFinalProgram(0.0f, 0.0f, 1.0f, false));
         FloatImage photonImage = FloatImage::FlipY(runFinalProgram(0.0f, 1.0f, 0.0f, false));
         photonImage *= param;
@@ -319,6 +328,13 @@ public:
         FloatImage::Save(mCombined, mDumpCombineFilename);
         FloatImage::Save(lightSourceImage + vplImage, mDumpWeightedVplFilename);
         FloatImage::Save(photonImage, mDumpWeightedPhotonFilename);
+    }
+
+    // iterations accumulated into the layers (after reduce(): over all ranks); equals numIterations on a single rank
+    int64_t accumulatedIterations() {
+        int64_t n = 0;
+        check(evplp_iterations(mHandle, &n), "evplp_iterations");
+        return n > 0 ? n : 1;
     }
 
     void writeFrame() {  // writeEveryFrame (:1079-1102)

@@ -81,9 +81,10 @@ public:
             check(evplp_gbuffer(mHandle), "evplp_gbuffer");                                // runDeferredProgram
             check(evplp_path_trace(mHandle, nullptr, mNumMaxBounce), "evplp_path_trace");  // runOptixPtProgram
             check(evplp_light_pass(mHandle), "evplp_light_pass");                          // runLightProgram
+            check(evplp_add_iterations(mHandle, 1), "evplp_add_iterations");               // what finish() normalises by
         }
         mNumIterations++;
-        if (mTimelimitMs > 0 && mMasterWatch.timeMilliSec() >= mTimelimitMs) return false;
+        if (mMasterWatch.timeMilliSec() >= mTimelimitMs) return false;   // unconditional, like rtpt2.h
         return true;
     }
 
@@ -110,7 +111,9 @@ public:
         } else {
             FloatImage lightImage = runFinalProgram(0.0f, 1.0f, false);
             FloatImage ptImage = runFinalProgram(1.0f, 0.0f, false);
-            ptImage *= 1.0f / (float)mNumIterations;  // the reference divides (FloatImage::operator/=); same up to 1 ulp
+            int64_t accumulated = 0;   // iterations in the layer (over all ranks once reduced); = mNumIterations on one rank
+            check(evplp_iterations(mHandle, &accumulated), "evplp_iterations");
+            ptImage *= 1.0f / (float)(accumulated > 0 ? accumulated : 1);  // the reference divides (FloatImage::operator/=); same up to 1 ulp
             result = lightImage + ptImage;
         }
         FloatImage::Save(FloatImage::FlipY(result), mOutputFilename);

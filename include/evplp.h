@@ -194,15 +194,22 @@ int evplp_path_trace(evplp_handle h, const EvplpTile* tile, uint32_t maxBounces)
  * firstRecord/numRecords index the record window written by the last evplp_light_trace. */
 int evplp_photon_splat(evplp_handle h, uint64_t firstRecord, uint64_t numRecords, const EvplpTile* tile);
 
-/* replaces runLightProgram (rtcomphoton.h:839-855; shaders/light.*) */
+/* replaces runLightProgram (rtcomphoton.h:839-855, 985-995; shaders/light.*): the light mesh seen through the UN-jittered
+ * camera ("we don't jitter light source"); the light layer is overwritten with 1 where the closest surface is the light. */
 int evplp_light_pass(evplp_handle h);
+
+/* The number of iterations accumulated into the layers (the reference's numIterations, the 1 / N of runFinalProgram,
+ * rtcomphoton.h:1001, 1122): kept next to the layers on the device so that evplp_reduce sums it with them -- ranks that
+ * stop at different iteration counts (time limit) still normalise by what was actually rendered.  evplp_clear_accum zeroes it. */
+int evplp_add_iterations(evplp_handle h, int64_t n);
+int evplp_iterations(evplp_handle h, int64_t* n);
 
 /* NEW (the reference is single-GPU): sum the accumulation layers over all ranks of
  * an NCCL communicator (ncclComm_t passed as void*).  Exact: the layers are int64. */
 int evplp_reduce(evplp_handle h, void* ncclComm);
 /* Device pointers + element counts of the accumulation layers, so a host that already
  * owns a communicator (e.g. torch.distributed) can all-reduce them itself.
- * layer: 0 = VPL int64[W*H*3], 1 = photon int64[W*H*3], 2 = light uint32->int64[W*H]. */
+ * layer: 0 = VPL int64[W*H*3], 1 = photon int64[W*H*3], 2 = light uint32[W*H], 3 = iteration count int64[1]. */
 int evplp_accum_layer(evplp_handle h, int layer, void** devPtr, uint64_t* numInt64);
 
 /* replaces runFinalProgram + dumpImage (rtcomphoton.h:756-787, 225-249; shaders/final.frag):
@@ -248,6 +255,10 @@ int evplp_launch_count(evplp_handle h, uint64_t* count);
 /* Tuning counters since the last evplp_reset_stats: [0] (warp, VPL) steps of the shaft gather, [1] steps that fell back to the
  * per-ray packet traversal, [2] 32-wide nodes visited, [3] candidate leaves tested, [4] 4-wide nodes, [5] 32-wide nodes. */
 int evplp_debug_counters(evplp_handle h, uint64_t out[8]);
+/* Cluster gather (gather_algo 1) since the last evplp_reset_stats, filled only by a tuning build (-DEVPLP_GATHER_HIST):
+ * [0..6] descents that collected 0 / <= 8 / <= 32 / <= 64 / <= 128 / <= 512 / more candidate leaves, [8] (cluster, tile) pairs,
+ * [9] of which some VPL lights the tile, [10] such VPLs.  evplp_debug_counters [6], [7] = descents, candidate batches. */
+int evplp_debug_cluster_hist(evplp_handle h, uint64_t out[16]);
 /* CUDA events on the handle's stream (4 slots): device-side timing of any span of calls. */
 int evplp_event_record(evplp_handle h, int slot);
 int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
@@ -266,7 +277,15 @@ int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
  * tile per warp of a full grid), "gather_lpt" (default 1: the tiles are drawn in descending order of the cycles they took in the
  * previous launch of the same grid -- longest processing time first; results do not depend on the order),
  * "bvh_leaf_max" / "shaft_leaf_max" (before evplp_build_bvh), "gather_min_blocks", "splat_mode" (0 tiled, 1 scatter),
- * "splat_group", "splat_max_entries": kernel variants.  Options are process-wide; the handle may be NULL. */
+ * "splat_group", "splat_max_entries": kernel variants.
+ * "gather_algo": the VPL-cluster gather (gather_fast.cu: the usable VPLs in Morton order, clusters of "gather_cluster_size"
+ * <= 16, one double-shaft descent per (cluster, 8x4-pixel tile) where the shaft is thin enough, shading tail with FMA
+ * contraction: radiance within the 1e-4 tolerance, NOT bit-identical to the oracle) is used 1 (default) = from 16384 usable
+ * VPLs on (it needs dense VPLs), 2 = always, 0 = never (the per-VPL exact-order kernel).  gather_chunks = 1 always selects
+ * the exact-order kernel (the bit-exact test mode).  Under gather_algo 1 the image partition
+ * ("gather_band_stride" / "gather_band_offset") is by 8x4-pixel tiles t = offset (mod stride) instead of 16-row bands.
+ * Every handle owns its options: a non-NULL handle sets that handle only; a NULL handle sets the defaults that handles
+ * created AFTERWARDS start from.  Values are range-checked (EVPLP_ERR_INVALID). */
 int evplp_set_option(evplp_handle h, const char* name, int value);
 
 #ifdef __cplusplus

@@ -332,12 +332,19 @@ void orc_photon_splat(const EvplpParams* P, int32_t W, int32_t H, const float* p
 }
 
 // light layer: count[i] += 1 where the nearest surface is the light mesh (rtcomphoton.h:839-855)
-void orc_light_pass(void* h, int32_t W, int32_t H, const int32_t* primIds, uint32_t* lightCount) {
+// runLightProgram (rtcomphoton.h:839-855, 985-995): the light mesh through the UN-jittered camera ("we don't jitter light
+// source"), nearest surface wins; the mask is written (1 / 0), not accumulated.
+void orc_light_pass(void* h, const EvplpParams* params, int32_t W, int32_t H, uint32_t* light) {
     Scene* s = (Scene*)h;
-    for (int64_t i = 0; i < (int64_t)W * H; i++) {
-        int p = primIds[i];
-        if (p >= s->lightFirst && p < s->lightFirst + s->lightCount) lightCount[i] += 1;
-    }
+    EvplpParams P = *params;
+    P.jitter[0] = 0.f; P.jitter[1] = 0.f;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const F3 dir = primary_dir(P, W, H, x, y);
+            const Hit hit = trace_closest(*s, getv(P.cameraPosition), dir, P.nearDist, P.farDist);
+            light[(size_t)y * W + x] = (hit.prim >= s->lightFirst && hit.prim < s->lightFirst + s->lightCount) ? 1u : 0u;
+        }
 }
 
 // final.frag:19-35 on the fixed-point layers; rows bottom-up (glReadPixels order).

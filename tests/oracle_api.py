@@ -58,7 +58,7 @@ def load():
     lib.orc_accumulate_fixed.argtypes = [_P, C.c_int64, _P]
     lib.orc_photon_splat.argtypes = [C.POINTER(capi.Params), C.c_int32, C.c_int32, _P, _P, _P, C.c_uint64, C.c_uint64,
                                      C.POINTER(capi.Tile), _P, _P, C.c_int32]
-    lib.orc_light_pass.argtypes = [_P, C.c_int32, C.c_int32, _P, _P]
+    lib.orc_light_pass.argtypes = [_P, C.POINTER(capi.Params), C.c_int32, C.c_int32, _P]
     lib.orc_resolve.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P]
     lib.orc_trace_rays.argtypes = [_P, _P, C.c_uint64, C.c_int32, _P, _P]
     lib.orc_lbvh.argtypes = [_P, _P, _P, _P, _P, _P, _P, _P]
@@ -123,8 +123,8 @@ class OracleScene:
                                   capi.ptr(accum), capi.ptr(counters), 1 if brute_force else 0)
         return counters
 
-    def light_pass(self, W, H, prims, light):
-        self.lib.orc_light_pass(self.h, W, H, capi.ptr(prims), capi.ptr(light))
+    def light_pass(self, params, W, H, light):
+        self.lib.orc_light_pass(self.h, C.byref(params), W, H, capi.ptr(light))
 
     def resolve(self, W, H, vpl, photon, light, vs, ps, ls, gamma=False):
         out = np.empty((H, W, 3), dtype=np.float32)

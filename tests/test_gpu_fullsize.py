@@ -54,15 +54,29 @@ def test_gather_tiles_and_chunks_at_1080p(conf):
         dev.vpl_gather(capi.GATHER_VPL, tile=tile)
     parts, _, _ = dev.download_accum()
     assert np.array_equal(parts, whole)  # ragged image tiles (multi-GPU partition) reproduce the whole frame exactly
+    dev.set_option("gather_algo", 0)   # exact-order kernel, VPL list in 3 ranges
     dev.set_option("gather_chunks", 3)
     dev.clear_accum()
     dev.vpl_gather(capi.GATHER_VPL)
     chunked, _, _ = dev.download_accum()
     dev.set_option("gather_chunks", 0)
+    dev.set_option("gather_algo", 1)
     a, b = chunked.astype(np.float64), whole.astype(np.float64)
     # 1e-5 relative (north_star bar: 1e-4) + 4 units of the Q31.32 quantum (each chunk rounds its partial sum once)
     assert (np.abs(a - b) <= 4 + 1e-5 * np.abs(b)).all()
     conf["whole_vpl"] = whole
+    # the default gather (VPL clusters, Morton summation order, FMA-contracted shading tail): whole frame at 1080p against
+    # the exact-order frame -- per-pixel radiance within 1e-4 relative (north_star) and image relative RMSE <= 1e-5
+    dev.set_option("gather_algo", 2)
+    dev.clear_accum()
+    dev.vpl_gather(capi.GATHER_VPL)
+    dev.set_option("gather_algo", 1)
+    fast, _, _ = dev.download_accum()
+    a = fast.astype(np.float64)
+    scale = np.abs(b).mean()
+    rel = np.abs(a - b) / (np.abs(b) + 1e-3 * scale)
+    assert rel.max() <= 1e-4, rel.max()
+    assert np.sqrt(np.mean((a - b) ** 2)) / scale <= 1e-5
 
 
 def test_gather_crop_matches_oracle_bit_for_bit(conf):

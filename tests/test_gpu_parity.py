@@ -170,11 +170,13 @@ def test_vpl_gather_all_mis_modes(rig, mis, gather_mode):
     assert np.array_equal(vpl, eacc)
     st = rig.dev.stats()
     assert st.gatherPairs == int(cnt[0]) and st.shadowRays == int(cnt[1])
-    # (b) VPL list split across blocks: same image within rounding of the partial sums
+    # (b) VPL list split across blocks (exact-order kernel, gather_algo 0): same image within rounding of the partial sums
+    rig.dev.set_option("gather_algo", 0)
     rig.dev.set_option("gather_chunks", 5)
     rig.dev.vpl_gather(capi.GATHER_VPL)
     vpl5, _, _ = rig.dev.download_accum()
     rig.dev.set_option("gather_chunks", 0)
+    rig.dev.set_option("gather_algo", 1)
     rig.dev.set_option("gather_mode", 1)  # back to the default
     a, b = vpl5.astype(np.float64), eacc.astype(np.float64)
     assert (np.abs(a - b) <= 6 + 1e-5 * np.abs(b)).all()  # 1e-5 relative + a few Q31.32 quanta (one rounding per chunk)
@@ -202,6 +204,7 @@ def test_chunked_gather_equals_the_oracle_chunk_by_chunk(rig, chunks):
         exp, _ = rig.orc.vpl_gather(P, W, H, planes, prims, sub, capi.GATHER_VPL)
         rig.orc.accumulate_fixed(exp, eacc)
     assert eacc.sum() > 0
+    rig.dev.set_option("gather_algo", 0)   # the exact-order kernel (the cluster gather sums in Morton order: test_gpu_cluster.py)
     rig.dev.set_option("gather_chunks", chunks)
     try:
         for _ in range(2):  # twice: the result does not depend on the order the atomics land in
@@ -210,6 +213,7 @@ def test_chunked_gather_equals_the_oracle_chunk_by_chunk(rig, chunks):
             assert np.array_equal(vpl, eacc)
     finally:
         rig.dev.set_option("gather_chunks", 0)
+        rig.dev.set_option("gather_algo", 1)
 
 
 def test_vpl_gather_accumulates_and_tiles(rig):
@@ -334,7 +338,7 @@ def test_full_iterations_accumulate_and_resolve(rig):
         img, _ = rig.orc.vpl_gather(P, W, H, planes, prims, rec, capi.GATHER_VPL)
         rig.orc.accumulate_fixed(img, ev)
         rig.orc.photon_splat(P, W, H, planes, prims, rec, 0, len(rec), ep)
-        rig.orc.light_pass(W, H, prims, el)
+        rig.orc.light_pass(P, W, H, el)
     rig.dev.set_option("gather_chunks", 0)
     vpl, photon, light = rig.dev.download_accum()
     assert np.array_equal(vpl, ev) and np.array_equal(photon, ep) and np.array_equal(light, el)

@@ -38,7 +38,7 @@ def _render(rank, world):
             img, _ = orc.vpl_gather(P, W, H, planes, prims, rec, capi.GATHER_VPL)
             orc.accumulate_fixed(img, vpl)
             orc.photon_splat(P, W, H, planes, prims, rec, 0, len(rec), photon)
-            orc.light_pass(W, H, prims, light)
+            orc.light_pass(P, W, H, light)
         # every rank replays the schedule of every iteration (rtcomphoton.h:1033-1063)
         host.evplp_host_progressive_update(k + 1, 0.7, 0.02, VPL_PATHS, PATHS, 0, capi.ptr(state))
     return vpl, photon, light, state
@@ -70,6 +70,7 @@ def test_round_robin_iterations_plus_allreduce_equal_single_rank(tmp_path):
     vpl, photon, light, state = _render(0, 1)
     assert np.array_equal(got["vpl"], vpl)
     assert np.array_equal(got["photon"], photon)
-    assert np.array_equal(got["light"], light.astype(np.int64))
+    # the light mask is written (un-jittered, the same in every iteration), so N ranks sum to N x mask: resolve tests != 0
+    assert np.array_equal(got["light"] != 0, light != 0)
     assert np.array_equal(got["state"], state)
     assert photon.sum() > 0 and vpl.sum() > 0
