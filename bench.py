@@ -302,7 +302,92 @@ def run_gpu(args):
     else:
         e2e_pairs = float(e2e[1])
 
+    # ---- side job 1: the same small job at every N, checksummed -- the reduced layers must be identical whatever N is
+    import zlib
+
+    def reduce_and_crc(t2):
+        h2 = t2.device_handle()
+        ck(lib.evplp_synchronize(h2), "sync")
+        crcs = []
+        for layer, typestr in ((0, "<i8"), (1, "<i8"), (2, "<i4"), (3, "<i8")):
+            p, n = C.c_void_p(), C.c_uint64()
+            ck(lib.evplp_accum_layer(h2, layer, C.byref(p), C.byref(n)), "accum_layer")
+
+            class _W:
+                __cuda_array_interface__ = {"shape": (n.value,), "typestr": typestr, "data": (p.value, False), "version": 2}
+
+            t = torch.as_tensor(_W(), device=f"cuda:{local_rank}")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            a = t.cpu().numpy()
+            crcs.append(zlib.crc32((a != 0).tobytes() if layer == 2 else a.tobytes()))   # light layer: a mask (N ranks write it)
+        return crcs
+
+    small = dict(PHOTONFAM, numLightPaths=20000, numVplLightPaths=128)
+    check = {}
+    t2 = HA.Technique(hs, small, 384, 216, device=local_rank, rank=rank, world_size=world)
+    for _ in range(8):                       # 8 iterations dealt round-robin: every rank of an 8-GPU run renders one
+        t2.iterate()
+    check["iterations_partition_crc32"] = reduce_and_crc(t2)
+    t2.close()
+    t3 = HA.Technique(hs, small, 384, 216, device=local_rank, rank=rank, world_size=world, image_partition=world > 1)
+    ck(lib.evplp_set_option(t3.device_handle(), b"gather_chunks", 2), "set_option")   # fixed VPL ranges: bit-equal for every N
+    for _ in range(2):
+        t3.iterate()
+    check["image_partition_crc32"] = reduce_and_crc(t3)
+    t3.close()
+
+    # ---- side job 2: ONE heavy frame split over the N GPUs (image tiles + light-path ranges, one all-reduce): strong scaling
+    single = None
+    if not args.no_single_frame:
+        hs4 = HA.HostScene.generate("buddha", 1, 8, 3840 / 2160)
+        fam4 = dict(PHOTONFAM, numVplLightPaths=1024, numLightPaths=300000)
+        t4 = HA.Technique(hs4, fam4, 3840, 2160, device=local_rank, rank=rank, world_size=world, image_partition=world > 1)
+        h4 = t4.device_handle()
+        lay = []
+        for layer, typestr in ((0, "<i8"), (1, "<i8"), (2, "<i4"), (3, "<i8")):
+            p, n = C.c_void_p(), C.c_uint64()
+            ck(lib.evplp_accum_layer(h4, layer, C.byref(p), C.byref(n)), "accum_layer")
+
+            class _W4:
+                __cuda_array_interface__ = {"shape": (n.value,), "typestr": typestr, "data": (p.value, False), "version": 2}
+
+            lay.append(torch.as_tensor(_W4(), device=f"cuda:{local_rank}"))
+
+        def frame():
+            t4.iterate()
+            ck(lib.evplp_synchronize(h4), "sync")
+            if world > 1:
+                for t in lay:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            frame()                          # warm-up (the second one already draws its tiles longest-first)
+        if world > 1:
+            dist.barrier()
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            frame()
+            if world > 1:
+                dist.barrier()
+            times.append(time.perf_counter() - t0)
+        ms4 = C.c_float()
+        ck(lib.evplp_last_stage_ms(h4, capi.STAGE_GATHER, C.byref(ms4)), "stage_ms")
+        fr = torch.tensor([float(np.mean(times)), ms4.value, -ms4.value], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(fr, op=dist.ReduceOp.MAX)
+        single = {"workload": "buddha-like statue scene 1.06 M triangles, 3840x2160, numVplLightPaths=1024, numLightPaths=300000: ONE "
+                              "iteration split over the GPUs by 8x4-pixel tiles (gather) and light-path ranges (splat), one all-reduce",
+                  "frame_ms": float(fr[0]) * 1e3, "gather_ms_slowest_rank": float(fr[1]), "gather_ms_fastest_rank": -float(fr[2]),
+                  "n_gpus": world, "timing": "wall clock around iterate + all-reduce + barrier, mean of 3 frames, max over ranks"}
+        t4.close()
+
     if rank == 0:
+        dbg0 = (C.c_uint64 * 8)()
+        ck(lib.evplp_debug_counters(h, dbg0), "debug_counters")
+        dbg_cluster = bool(dbg0[6])   # the cluster gather ran (it starts at 16384 usable VPLs)
         hbm, sm_max, how = peaks()
         gather_s = stage_ms[2] / 1e3
         splat_s = max(stage_ms[3] / 1e3, 1e-9)
@@ -312,12 +397,13 @@ def run_gpu(args):
         # DRAM traffic of one gather launch of the HEADLINE workload from the committed ncu capture (a profiling override
         # runs a different launch: null)
         traffic, traffic_src = None, ""
-        tpath = os.path.join(ROOT, "profiles", "r1_gather_traffic_headline_v9.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_gather_traffic_headline.json")
         overridden = WORKLOAD.startswith("NON-HEADLINE") or bool(args.opt)
         if not overridden and os.path.exists(tpath):
             traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
             traffic_src = ("; traffic = dram__bytes_read + dram__bytes_write of one launch of this workload "
-                           "(profiles/r1_gather_traffic_headline_v9.json): BVH nodes and triangles missing the L2 over 6 s, 1.3 GB/s")
+                           "(profiles/r2_gather_traffic_headline.json: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of that "
+                           "launch): G-buffer planes, prepared VPLs, accumulators and whatever BVH data misses the L2")
         nrec = PHOTONFAM["numLightPaths"] * 4
         splat_bytes = (96.0 * nrec + 64.0 * RES_X * RES_Y + 48.0 * RES_X * RES_Y) * args.steps
         line = {
@@ -334,16 +420,18 @@ def run_gpu(args):
             "ms_per_iteration": sec * 1e3 / args.steps,
             "stage_ms_per_step_rank0": {"gbuffer": stage_ms[0] / args.steps, "light_trace": stage_ms[1] / args.steps,
                                         "vpl_gather": stage_ms[2] / args.steps, "photon_splat": stage_ms[3] / args.steps},
-            "roofline": {"kernel": "gather_vpl_kernel<4, true> (shaft gather)", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp32_peak, "traffic": traffic,
+            "roofline": {"kernel": "gather_cluster_kernel<1, 3> (VPL-cluster gather, gather_fast.cu)" if dbg_cluster else
+                                   "gather_vpl_kernel<4, true> (per-VPL shaft gather)", "bound": "fp32", "achieved": ach, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": traffic,
                          "note": f"{FLOP_PER_PAIR:.0f} algorithmic FP32 flop per pair (SURVEY 8d) x pairs / gather kernel time; peak = "
-                                 f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz ({how} clock); the kernel is shadow-ray traversal bound, "
-                                 "not HBM or tensor bound (ncu, profiles/r1_gather_vpl_v9_ncu_full_summary.txt: 68 % of peak "
-                                 "instruction issue, ALU pipe 43 %, FMA pipe 26 %, DRAM 0.04 %)" + traffic_src},
+                                 f"148 SM x 128 lanes x 2 x {sm_max:.0f} MHz ({how} clock); the kernel is bound by the shadow-ray "
+                                 "visibility work (descents of the 32-wide hierarchy, candidate-leaf slab and triangle tests), not by "
+                                 "HBM or tensor throughput: ncu summaries under profiles/ (r2_gather_cluster_*)" + traffic_src},
             "roofline_splat": {"kernel": "splat_prepare + splat_fill + splat_tile_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
                                "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": None,
                                "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}"},
             "clocks": clk, "gpu_launches": int(l1 - l0),
+            "same_job_checksums": check, "single_frame_strong_scaling": single,
             "e2e": {"value": e2e_pairs / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 3200 + C.sizeof(capi.Params),
                     "d2h_bytes_per_step": RES_X * RES_Y * 12 + 16},
         }
@@ -397,6 +485,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="evplp_b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single-frame", action="store_true", help="skip the single-frame strong-scaling side job (4K statue frame)")
     # profiling aids only (ncu replays every kernel ~40 times): the headline workload is the default
     ap.add_argument("--vpl-paths", type=int, default=None, help="override numVplLightPaths (profiling only)")
     ap.add_argument("--light-paths", type=int, default=None, help="override numLightPaths (profiling only)")

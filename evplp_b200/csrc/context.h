@@ -162,7 +162,35 @@ struct GatherParams {
     unsigned vgx, vgy, vgz;
     int persistent;
     int shaftStreak, shaftSkip;  // shaft gather: overflows in a row before, and number of, steps sent straight to the packet traversal
+    // persistent VPL gather: this handle's share of the image = the 8x4-pixel tiles t = tOffset + k * tStride, k < ownedTiles, of a
+    // row-major numbering with row pitch pitchX (one phantom tile per row when tilesX is a multiple of the stride, so that
+    // consecutive rows do not give a handle the same columns); work item v = chunk * ownedTiles + k
+    int tilePartition, tilesX, pitchX;
+    uint32_t ownedTiles, tStride, tOffset;
 };
+
+struct TileShare { int tilesX, pitchX; uint32_t ownedTiles, stride, offset; uint64_t pixels; };
+// the tiles of rectangle t that belong to this handle (gather_band_stride / gather_band_offset) and their pixel count
+inline TileShare tile_share(const EvplpContext* c, EvplpTile t) {
+    TileShare s;
+    const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
+    s.stride = c->opt.bandStride > 0 ? (uint32_t)c->opt.bandStride : 1u;
+    s.offset = c->opt.bandStride > 0 ? (uint32_t)c->opt.bandOffset : 0u;
+    s.tilesX = (tw + 7) / 8;
+    const int tilesY = (th + 3) / 4;
+    s.pitchX = (s.stride > 1 && s.tilesX % (int)s.stride == 0) ? s.tilesX + 1 : s.tilesX;
+    const uint32_t total = (uint32_t)s.pitchX * (uint32_t)tilesY;
+    s.ownedTiles = s.offset < total ? (total - s.offset + s.stride - 1) / s.stride : 0u;
+    s.pixels = 0;
+    for (uint32_t k = 0; k < s.ownedTiles; k++) {
+        const uint32_t tt = s.offset + k * s.stride;
+        const int ty = (int)(tt / (uint32_t)s.pitchX), tx = (int)(tt % (uint32_t)s.pitchX);
+        if (tx >= s.tilesX) continue;
+        const int w = tw - tx * 8 < 8 ? tw - tx * 8 : 8, h = th - ty * 4 < 4 ? th - ty * 4 : 4;
+        s.pixels += (uint64_t)w * (uint64_t)h;
+    }
+    return s;
+}
 
 // gather_fast.cu: the VPL-cluster gather (tolerance mode); `count` = usable VPLs in c->vplList (already compacted)
 cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile tile, GatherParams g, uint32_t count);

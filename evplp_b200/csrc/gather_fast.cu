@@ -646,28 +646,11 @@ cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile t, GatherParams g, 
     fp.count = count;
     fp.clusterSize = c->opt.clusterSize < 1 ? 1 : (c->opt.clusterSize > FG_CL_MAX ? FG_CL_MAX : c->opt.clusterSize);
     fp.numClusters = (count + (uint32_t)fp.clusterSize - 1) / (uint32_t)fp.clusterSize;
-    fp.stride = c->opt.bandStride > 0 ? (uint32_t)c->opt.bandStride : 1u;
-    fp.offset = c->opt.bandStride > 0 ? (uint32_t)c->opt.bandOffset : 0u;
-    fp.tilesX = (tw + 7) / 8;
+    const TileShare share = tile_share(c, t);
+    fp.stride = share.stride; fp.offset = share.offset; fp.tilesX = share.tilesX; fp.pitchX = share.pitchX; fp.ownedTiles = share.ownedTiles;
     fp.tileAngle = 8.0f * 2.0f * P.tanHalfFovX / (float)c->W;
-    const int tilesY = (th + 3) / 4;
-    // consecutive tiles go to consecutive handles; a row pitch that is a multiple of the stride would give every handle the
-    // same columns of the image, so one phantom tile (outside the image: skipped) is appended to such rows
-    fp.pitchX = (fp.stride > 1 && fp.tilesX % (int)fp.stride == 0) ? fp.tilesX + 1 : fp.tilesX;
-    const uint32_t totalTiles = (uint32_t)fp.pitchX * (uint32_t)tilesY;
-    fp.ownedTiles = fp.offset < totalTiles ? (totalTiles - fp.offset + fp.stride - 1) / fp.stride : 0u;
     if (fp.ownedTiles == 0) return cudaSuccess;
-    {   // pixels of this handle's tiles (statistics: pairs = pixels x usable VPLs)
-        uint64_t px = 0;
-        for (uint32_t k = 0; k < fp.ownedTiles; k++) {
-            const uint32_t tt = fp.offset + k * fp.stride;
-            const int ty = (int)(tt / (uint32_t)fp.pitchX), tx = (int)(tt % (uint32_t)fp.pitchX);
-            if (tx >= fp.tilesX) continue;
-            const int w = tw - tx * 8 < 8 ? tw - tx * 8 : 8, h = th - ty * 4 < 4 ? th - ty * 4 : 4;
-            px += (uint64_t)w * (uint64_t)h;
-        }
-        c->stats.gatherPairs += px * (uint64_t)count;
-    }
+    c->stats.gatherPairs += share.pixels * (uint64_t)count;
     if (count == 0) {
         // no usable VPL: the frame's contribution is zero (cleareveryframe still has to overwrite the layer)
         if (!P.doAccumulate) {

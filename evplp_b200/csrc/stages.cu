@@ -238,7 +238,7 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
     float4* batch = batchAll[warp];
     const uint32_t stackBase = opaque((uint32_t)__cvta_generic_to_shared(stacks[warp]));
     const uint32_t candBase = opaque((uint32_t)__cvta_generic_to_shared(cands[SHAFT ? warp : 0]));
-    const uint32_t vTotal = gp.vgx * gp.vgy * gp.vgz * GATHER_WARPS;
+    const uint32_t vTotal = gp.tilePartition ? gp.ownedTiles * gp.numChunks : gp.vgx * gp.vgy * gp.vgz * GATHER_WARPS;
     unsigned rays = 0;
     unsigned shaftCnt[3] = {0u, 0u, 0u}, shaftSteps = 0u;
     int ovf = 0;
@@ -254,11 +254,24 @@ gather_vpl_kernel(DevScene sc, GatherParams gp, const float4* __restrict__ gbuf,
         v = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * GATHER_WARPS + warp;
     }
     const long long itemStart = clock64();
-    const uint32_t vw = v % GATHER_WARPS, vb = v / GATHER_WARPS;
-    const uint32_t bx = vb % gp.vgx, by = (vb / gp.vgx) % gp.vgy, bz = vb / (gp.vgx * gp.vgy);
-    const int x = gp.x0 + bx * 16 + (vw & 1) * 8 + (lane & 7);
-    const int y = gp.y0 + (by * gp.bandStride + gp.bandOffset) * 16 + (vw >> 1) * 4 + (lane >> 3);
-    const bool inside = x < gp.x1 && y < gp.y1;
+    int x, y;
+    uint32_t bz;
+    bool inTile = true;
+    if (gp.tilePartition) {   // tile t = tOffset + k * tStride of the handle's share, VPL range bz
+        bz = v / gp.ownedTiles;
+        const uint32_t t = gp.tOffset + (v % gp.ownedTiles) * gp.tStride;
+        const int ty = (int)(t / (uint32_t)gp.pitchX), tx = (int)(t % (uint32_t)gp.pitchX);
+        x = gp.x0 + tx * 8 + (lane & 7);
+        y = gp.y0 + ty * 4 + (lane >> 3);
+        inTile = tx < gp.tilesX;
+    } else {
+        const uint32_t vw = v % GATHER_WARPS, vb = v / GATHER_WARPS;
+        const uint32_t bx = vb % gp.vgx, by = (vb / gp.vgx) % gp.vgy;
+        bz = vb / (gp.vgx * gp.vgy);
+        x = gp.x0 + bx * 16 + (vw & 1) * 8 + (lane & 7);
+        y = gp.y0 + (by * gp.bandStride + gp.bandOffset) * 16 + (vw >> 1) * 4 + (lane >> 3);
+    }
+    const bool inside = inTile && x < gp.x1 && y < gp.y1;
     const size_t n = (size_t)gp.W * gp.H;
     const size_t i = inside ? (size_t)y * gp.W + x : 0;
     float gw;
@@ -1126,7 +1139,10 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     if (mode == EVPLP_GATHER_VPL && c->opt.gatherChunks != 1 &&
         (c->opt.gatherAlgo == 2 || (c->opt.gatherAlgo == 1 && count >= 16384u)))
         return launch_gather_cluster(c, t, g, count);
-    c->stats.gatherPairs += (uint64_t)count * (uint64_t)tw * ownRows;
+    const bool tilePartition = mode == EVPLP_GATHER_VPL && c->opt.gatherPersistent;
+    const TileShare share = tile_share(c, t);
+    if (tilePartition && share.ownedTiles == 0) return cudaSuccess;
+    c->stats.gatherPairs += (uint64_t)count * (tilePartition ? share.pixels : (uint64_t)tw * ownRows);
     if (mode == EVPLP_GATHER_VSL) {
         c->stageBegin(ST_GATHER);
         gather_vsl_kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), g, c->skipMatrix.p, c->gbuf.p, c->records.p,
@@ -1140,8 +1156,9 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     if (c->opt.gatherChunks > 0) {
         chunks = (unsigned)c->opt.gatherChunks;
     } else {
-        const unsigned blocks = grid.x * grid.y;
-        const unsigned want = 148u * 3u * 6u;  // ~6 waves of resident blocks, so the tail wave stays short
+        // enough work items per resident warp that the tail stays short (small image shares: multi-GPU partition of one frame)
+        const unsigned blocks = tilePartition ? (share.ownedTiles + GATHER_WARPS - 1) / GATHER_WARPS : grid.x * grid.y;
+        const unsigned want = tilePartition ? 148u * 4u * 24u : 148u * 3u * 6u;
         if (blocks < want) chunks = (want + blocks - 1) / blocks;
         const unsigned maxChunks = (count + 4 * GATHER_BATCH - 1) / (4 * GATHER_BATCH);
         if (chunks > maxChunks) chunks = maxChunks ? maxChunks : 1;
@@ -1155,6 +1172,8 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
     }
     g.vgx = grid.x; g.vgy = grid.y; g.vgz = grid.z;
     g.persistent = c->opt.gatherPersistent;
+    g.tilePartition = tilePartition ? 1 : 0;
+    g.tilesX = share.tilesX; g.pitchX = share.pitchX; g.ownedTiles = share.ownedTiles; g.tStride = share.stride; g.tOffset = share.offset;
     g.shaftStreak = c->opt.shaftStreak > 0 ? c->opt.shaftStreak : 1;
     g.shaftSkip = c->opt.shaftSkip;
     uint32_t* tileCounter = c->counters.p + 2;  // (slots 0-2 belong to the BVH build, which is over by now)
@@ -1166,7 +1185,7 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
         if (e != cudaSuccess) return e;
         if (c->opt.gatherLpt) {
             // longest-processing-time-first: order the tiles by the cycles they took in the previous launch of this grid
-            const uint32_t vTotal = grid.x * grid.y * grid.z * GATHER_WARPS;
+            const uint32_t vTotal = tilePartition ? share.ownedTiles * chunks : grid.x * grid.y * grid.z * GATHER_WARPS;
             const uint64_t sig[4] = {((uint64_t)grid.x << 40) | ((uint64_t)grid.y << 20) | grid.z,
                                      ((uint64_t)(uint32_t)t.x0 << 32) | (uint32_t)t.y0, ((uint64_t)(uint32_t)t.x1 << 32) | (uint32_t)t.y1,
                                      ((uint64_t)(uint32_t)g.bandStride << 32) | (uint32_t)g.bandOffset};
@@ -1195,7 +1214,7 @@ cudaError_t launch_gather(EvplpContext* c, EvplpTile t, int mode) {
             tileCost = c->gatherCost.p;
         }
         const unsigned resident = 148u * 5u;  // at most 5 blocks of 256 threads fit an SM at any register count used here
-        const unsigned blocks = grid.x * grid.y * grid.z;
+        const unsigned blocks = tilePartition ? (share.ownedTiles * chunks + GATHER_WARPS - 1) / GATHER_WARPS : grid.x * grid.y * grid.z;
         lgrid = dim3(blocks < resident ? blocks : resident, 1, 1);
     }
     c->stageBegin(ST_GATHER);
