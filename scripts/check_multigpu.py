@@ -65,7 +65,8 @@ def main():
                 t1.close()
             mode = "image bands + path ranges" if image_partition else "iterations round-robin"
             for name, a, b in zip(("vpl", "photon", "light"), ls, ref):
-                same = bool(torch.equal(a, b))
+                # the light layer is a mask that every rendering rank writes (un-jittered, identical): compare what resolve tests
+                same = bool(torch.equal(a != 0, b != 0)) if name == "light" else bool(torch.equal(a, b))
                 print(f"[{mode}] layer {name}: N={world} reduce == 1-GPU: {same} (sum {int(a.sum())})")
                 ok &= same and (name == "light" or int(a.abs().sum()) > 0)  # the light may be outside the view
         t.close()
