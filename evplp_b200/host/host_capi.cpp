@@ -114,6 +114,31 @@ void* evplp_host_technique_create(void* s, const char* techniqueJson, int resX, 
     } catch (const std::exception& e) { g_hostErr = e.what(); return nullptr; }
 }
 
+// The multi-rank host logic without a device: parse the technique, then plan numIterations passes of the loop as rank `rank` of
+// `worldSize` would (RtComPhoton::planNext / advanceSchedule -- the same code iterate() runs).  out: 16 doubles per iteration =
+// iteration, render, jitter x, jitter y, rngSeed, photonRadius, clampingValue, pdfMc, vslRadius, vslInvPiRadius2,
+// splatFirstPath, splatNumPaths, tileStride, tileOffset, drawLight, countIteration.
+int evplp_host_technique_plan(void* s, const char* techniqueJson, int resX, int resY, int lvc, int rank, int worldSize, int partitionMode,
+                              int numIterations, double* out) {
+    GUARD(
+        HostScene* hs = (HostScene*)s;
+        std::unique_ptr<RtComPhoton> t(lvc ? new RtLvcComPhoton(0) : new RtComPhoton(0));
+        t->setPartition(rank, worldSize, partitionMode ? RtComPhoton::PartitionImage : RtComPhoton::PartitionIterations);
+        Vec2 res; res.x = (float)resX; res.y = (float)resY;
+        t->parse(hs->scene, res, Json::parse(techniqueJson));
+        t->setupHostOnly();
+        for (int k = 0; k < numIterations; k++) {
+            const RtComPhoton::IterationPlan p = t->planNext();
+            double* o = out + 16 * (size_t)k;
+            o[0] = p.iteration; o[1] = p.render; o[2] = p.jitter.x; o[3] = p.jitter.y; o[4] = p.rngSeed; o[5] = p.photonRadius;
+            o[6] = p.clampingValue; o[7] = p.pdfMc; o[8] = p.vslRadius; o[9] = p.vslInvPiRadius2; o[10] = (double)p.splatFirstPath;
+            o[11] = (double)p.splatNumPaths; o[12] = p.tileStride; o[13] = p.tileOffset; o[14] = p.drawLight; o[15] = p.countIteration;
+            t->advanceSchedule();
+        }
+        return 0;
+    )
+}
+
 void evplp_host_technique_set_max_paths_per_trace(void* t, uint64_t n) { ((HostTechnique*)t)->tech->setMaxPathsPerTrace(n); }
 
 void* evplp_host_technique_handle(void* t) { return ((HostTechnique*)t)->tech->handle(); }

@@ -248,42 +248,107 @@ public:
         }
     }
 
-    // One pass of the loop body (rtcomphoton.h:936-1068).  Returns false when the loop must stop.
-    bool iterate() {
-        if (mNumIterations == mNumMaxIteration) return false;
+    // What ONE pass of the loop body (rtcomphoton.h:936-1068) does on THIS rank: everything the host decides, nothing of the
+    // device.  planNext() draws the iteration's jitter and reads the schedule; execute() issues the stages through the C ABI;
+    // advanceSchedule() is the numIterations++ / progressive-update tail.  (Split so that the multi-rank host logic --
+    // which rank renders what, with which uniforms -- can be checked without a GPU: evplp_host_technique_plan.)
+    struct IterationPlan {
+        int iteration = 0;                 // k
+        bool render = false;               // this rank renders (its share of) iteration k
         Vec2 jitter;
+        uint32_t rngSeed = 0;              // k + rngOffset
+        float photonRadius = 0, clampingValue = 0, pdfMc = 0, vslRadius = 0, vslInvPiRadius2 = 0;
+        uint64_t splatFirstPath = 0, splatNumPaths = 0;   // light paths whose photons this rank splats
+        uint32_t tileStride = 1, tileOffset = 0;          // 8x4-pixel tiles t = offset (mod stride) this rank gathers
+        bool drawLight = false, countIteration = false;
+    };
+
+    bool imageMode() const { return mPartition == PartitionImage && mWorldSize > 1; }
+
+    IterationPlan planNext() {
+        IterationPlan p;
+        p.iteration = mNumIterations;
         if (mJitter) {
             Vec2 xi = mMainSampler->nextVec2();
-            jitter.x = (2.0f * xi.x - 1.0f) * mInvResolution.x;
-            jitter.y = (2.0f * xi.y - 1.0f) * mInvResolution.y;
+            p.jitter.x = (2.0f * xi.x - 1.0f) * mInvResolution.x;
+            p.jitter.y = (2.0f * xi.y - 1.0f) * mInvResolution.y;
         }
-        const bool imageMode = mPartition == PartitionImage && mWorldSize > 1;
-        const bool mine = imageMode || (mNumIterations % mWorldSize) == mRank;  // iteration partition over GPUs
-        if (mine) {
-            pushParams(jitter, (uint32_t)mNumIterations + mRngOffset);
-            if (mFrameMode == ClearEveryFrame) check(evplp_clear_accum(mHandle), "evplp_clear_accum");
-            if (mDoDeferredShading) runDeferredProgram();
-            if ((uint64_t)mNumLightPaths <= mMaxPathsPerTrace) {
-                if (mDoLightTracing) runOptixLightTracingProgram((uint32_t)mNumIterations + mRngOffset);
-                if (mDoVplSplat) runOptixVplProgram();
-                if (mDoPhotonSplat) runPhotonSplat();
-            } else {
-                runStreamed((uint32_t)mNumIterations + mRngOffset);
-            }
-            if (mDoLightRender && (!imageMode || mRank == 0)) runLightProgram();
-            // one more iteration sits in the layers (image partition: every rank holds a share of it, rank 0 counts it)
-            if (!imageMode || mRank == 0) check(evplp_add_iterations(mHandle, 1), "evplp_add_iterations");
+        p.render = imageMode() || (mNumIterations % mWorldSize) == mRank;  // iteration partition: k = rank (mod N)
+        p.rngSeed = (uint32_t)mNumIterations + mRngOffset;
+        p.photonRadius = mPhotonRadius; p.clampingValue = mClampingValue; p.pdfMc = mPrecomptedPdfMc;
+        p.vslRadius = mVslRadius; p.vslInvPiRadius2 = mVslInvPiRadius2;
+        p.splatFirstPath = 0; p.splatNumPaths = mNumLightPaths;
+        if (imageMode()) {  // this rank splats its contiguous range of light paths and gathers every Nth tile
+            p.splatFirstPath = (uint64_t)mNumLightPaths * (uint64_t)mRank / (uint64_t)mWorldSize;
+            p.splatNumPaths = (uint64_t)mNumLightPaths * (uint64_t)(mRank + 1) / (uint64_t)mWorldSize - p.splatFirstPath;
+            p.tileStride = (uint32_t)mWorldSize; p.tileOffset = (uint32_t)mRank;
         }
+        p.drawLight = mDoLightRender && (!imageMode() || mRank == 0);
+        p.countIteration = !imageMode() || mRank == 0;   // image partition: every rank holds a share of it, rank 0 counts it
+        return p;
+    }
+
+    void execute(const IterationPlan& p) {
+        pushParams(p.jitter, p.rngSeed);
+        if (mFrameMode == ClearEveryFrame) check(evplp_clear_accum(mHandle), "evplp_clear_accum");
+        if (mDoDeferredShading) runDeferredProgram();
+        if ((uint64_t)mNumLightPaths <= mMaxPathsPerTrace) {
+            if (mDoLightTracing) runOptixLightTracingProgram(p.rngSeed);
+            if (mDoVplSplat) runOptixVplProgram();
+            if (mDoPhotonSplat) runPhotonSplat();
+        } else {
+            runStreamed(p.rngSeed);
+        }
+        if (p.drawLight) runLightProgram();
+        if (p.countIteration) check(evplp_add_iterations(mHandle, 1), "evplp_add_iterations");
+    }
+
+    void advanceSchedule() {
         mNumIterations++;
-        if (mNumIterations % 20 == 0 && mRank == 0) {
-            float currentTiming = mMasterWatch.timeMilliSec();
-            std::cout << "numIter: " << mNumIterations << " | raduis: " << mPhotonRadius << " | clamping: " << mClampingValue
-                      << " | timing: " << currentTiming - mPrevTiming << "\n";
-            mPrevTiming = currentTiming;
-        }
         if (mDoProgressive) {
             ProgressiveUpdate(mNumIterations, mAlphaProgressive, mClampingStart, mNumVplLightPaths, mNumLightPaths, mForceVsl,
                               &mPhotonRadius, &mClampingValue, &mPrecomptedPdfMc, &mVslRadius, &mVslInvPiRadius2);
+        }
+    }
+
+    // planning without a device: what setup() prepares of the host state
+    void setupHostOnly() {
+        mMainSampler.reset(new IndependentSampler(mRngOffset));
+        mNumIterations = 0;
+        if (mFrameMode == ClearEveryFrame && mWorldSize > 1 && !imageMode())
+            throw std::runtime_error("frameMode cleareveryframe with several ranks needs the image partition (PartitionImage)");
+    }
+
+    // One pass of the loop body (rtcomphoton.h:936-1068).  Returns false when the loop must stop.
+    bool iterate() {
+        if (mNumIterations == mNumMaxIteration) return false;
+        const IterationPlan p = planNext();
+        if (p.render) execute(p);
+        const bool report = (mNumIterations + 1) % 20 == 0 && mRank == 0;
+        const float radiusBefore = mPhotonRadius, clampBefore = mClampingValue;
+        advanceSchedule();
+        if (report) {
+            float currentTiming = mMasterWatch.timeMilliSec();
+            const float prevTimingForAdvice = mPrevTiming;
+            std::cout << "numIter: " << mNumIterations << " | raduis: " << radiusBefore << " | clamping: " << clampBefore
+                      << " | timing: " << currentTiming - mPrevTiming << "\n";
+            mPrevTiming = currentTiming;
+            // targetRenderingTime (rtcomphoton.h:1017-1030): advice printed with the 20-iteration report, never applied.
+            // frameTime = the time of those 20 iterations / 20 (rtcomphoton.h:1010-1012).
+            if (mTargetRenderingTime != -1.f) {
+                const float frameTime = (currentTiming - prevTimingForAdvice) / 20.0f;
+                const float factor = mTargetRenderingTime / frameTime;
+                if (factor != 1.f) {
+                    std::cout << "change number of samples: " << factor << " | currFrame time: " << frameTime << "\n";
+                    if (mNumVplLightPaths != 0) {
+                        const int newNbVPL = (int)(mNumVplLightPaths * factor);
+                        std::cout << "Nb light paths: " << newNbVPL * (mNumLightPaths / mNumVplLightPaths) << "\n";
+                        std::cout << "Nb VPL paths: " << newNbVPL << "\n";
+                    } else {
+                        std::cout << "Nb light paths: " << mNumLightPaths * factor << "\n";
+                    }
+                }
+            }
         }
         // rtcomphoton.h:1065 compares unconditionally (a non-positive limit ends the run after one iteration).  With several ranks
         // each rank watches its own clock and may leave the loop at a different iteration; finish() normalises by the number

@@ -66,6 +66,7 @@ def load_host_library():
     lib.evplp_host_technique_create.restype = _P
     lib.evplp_host_technique_create.argtypes = [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.evplp_host_technique_set_max_paths_per_trace.argtypes = [_P, C.c_uint64]
+    lib.evplp_host_technique_plan.argtypes = [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]
     lib.evplp_host_technique_handle.restype = _P
     lib.evplp_host_technique_handle.argtypes = [_P]
     lib.evplp_host_technique_iterate.argtypes = [_P]
@@ -265,6 +266,21 @@ class PathTracer:
             self.close()
         except Exception:
             pass
+
+
+PLAN_FIELDS = ("iteration", "render", "jitter_x", "jitter_y", "rngSeed", "photonRadius", "clampingValue", "pdfMc", "vslRadius",
+               "vslInvPiRadius2", "splatFirstPath", "splatNumPaths", "tileStride", "tileOffset", "drawLight", "countIteration")
+
+
+def plan(host_scene, photonfam, res_x, res_y, rank, world_size, num_iterations, image_partition=False, lvc=False):
+    """What rank `rank` of `world_size` does in each of the first `num_iterations` passes of RtComPhoton's loop (the host logic
+    of iterate(), no device): a list of dicts with PLAN_FIELDS."""
+    lib = load_host_library()
+    out = np.zeros((num_iterations, 16), dtype=np.float64)
+    if lib.evplp_host_technique_plan(host_scene.h, json.dumps(photonfam).encode(), res_x, res_y, 1 if lvc else 0, rank, world_size,
+                                     1 if image_partition else 0, num_iterations, capi.ptr(out)) != 0:
+        _err(lib, "evplp_host_technique_plan")
+    return [dict(zip(PLAN_FIELDS, row)) for row in out]
 
 
 def export_scene(name, out_dir, seed=1, detail=8, res_x=1280, res_y=720):
