@@ -86,7 +86,28 @@ public:
         return result / numPixels;
     }
 
+    // Masked error metrics.  The reference ships scene/conference/conference_mask.png with the note that the error metric of
+    // the conference scene (the only one with a visible light source, which is not anti-aliased) must be computed under it
+    // (scene/conference/README.md:1-2); the metric code itself (floatimage.cpp:64-112) takes no mask, so the weighting is
+    // ours: weight = mask value / 255 (white = counted, black = the light), result = sum(w * err) / sum(w).  `mask` holds one
+    // weight per pixel in the images' row order.
+    static float ComputeMse(const FloatImage& a, const FloatImage& ref, const std::vector<float>& mask) { return masked(a, ref, mask, false); }
+    static float ComputeRelMse(const FloatImage& a, const FloatImage& ref, const std::vector<float>& mask) { return masked(a, ref, mask, true); }
+
 private:
+    static float masked(const FloatImage& a, const FloatImage& ref, const std::vector<float>& mask, bool relative) {
+        if (a.mWidth != ref.mWidth || a.mHeight != ref.mHeight || mask.size() != a.mWidth * a.mHeight)
+            throw std::runtime_error("FloatImage: image and mask sizes differ");
+        float result = 0, weight = 0;
+        for (size_t p = 0; p < a.mWidth * a.mHeight; p++) {
+            float r0 = ref.mData[3 * p], r1 = ref.mData[3 * p + 1], r2 = ref.mData[3 * p + 2];
+            float d0 = a.mData[3 * p] - r0, d1 = a.mData[3 * p + 1] - r1, d2 = a.mData[3 * p + 2] - r2;
+            float e = d0 * d0 + d1 * d1 + d2 * d2;
+            if (relative) e = e / (r0 * r0 + r1 * r1 + r2 * r2 + 0.001f);
+            result += mask[p] * e; weight += mask[p];
+        }
+        return weight > 0 ? result / weight : 0.f;
+    }
     size_t mWidth = 0, mHeight = 0;
     std::vector<float> mData;
 };

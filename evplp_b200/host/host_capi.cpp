@@ -10,6 +10,7 @@
 #include "rtpt2.h"
 #else
 #include "rtcommon.h"
+#include "realtime.h"
 #endif
 #include "scenegen.h"
 
@@ -226,6 +227,17 @@ float evplp_host_pfm_relmse(const char* a, const char* b) {
     try { return FloatImage::ComputeRelMse(FloatImage::LoadPFM(a), FloatImage::LoadPFM(b)); }
     catch (const std::exception& e) { g_hostErr = e.what(); return -1.f; }
 }
+// masked metrics (scene/conference/README.md): `maskPng` is read through the PNG decoder, first channel / 255 = weight; PFM files
+// are stored bottom-up and loaded top-down, the mask is top-down like the PNG.  relative = 0: MSE, 1: relMSE.  -1 on error.
+float evplp_host_pfm_masked_error(const char* a, const char* b, const char* maskPng, int relative) {
+    try {
+        const FloatImage ia = FloatImage::LoadPFM(a), ib = FloatImage::LoadPFM(b);
+        const png::Image m = png::DecodeFile(maskPng, 1);
+        std::vector<float> w(m.pixels.size());
+        for (size_t i = 0; i < w.size(); i++) w[i] = (float)m.pixels[i] / 255.0f;
+        return relative ? FloatImage::ComputeRelMse(ia, ib, w) : FloatImage::ComputeMse(ia, ib, w);
+    } catch (const std::exception& e) { g_hostErr = e.what(); return -1.f; }
+}
 
 
 // Host-only configuration check: reads a scene JSON file exactly as main.cpp / LoadScene / the techniques' parse() do, but
@@ -286,6 +298,33 @@ int evplp_host_jpeg_decode(const uint8_t* data, uint64_t n, uint8_t* rgbOut, uin
     GUARD(jpeg::Image img; jpeg::Decode(data, (size_t)n, &img);
           if (img.rgb.size() > rgbCapacity) throw std::runtime_error("evplp_host_jpeg_decode: output buffer too small");
           memcpy(rgbOut, img.rgb.data(), img.rgb.size()); return 0;)
+}
+// RealTime::loop contract probe (common/realtime.h:100-141): beforeSwap returns true `beforeTrue` times, afterSwap returns true
+// `afterTrue` times, the sink reports "window closed" once `closeAfter` frames were presented (< 0: never).
+// out = {loop passes, frames presented, afterSwap calls}
+void evplp_host_realtime_probe(int beforeTrue, int afterTrue, int closeAfter, uint64_t out[3]) {
+    struct Probe : RealTime::Sink {
+        int closeAfter; uint64_t presented = 0;
+        void present(uint64_t) override { presented++; }
+        bool shouldClose() override { return closeAfter >= 0 && presented >= (uint64_t)closeAfter; }
+    } probe;
+    probe.closeAfter = closeAfter;
+    RealTime rt(&probe);
+    int b = 0, a = 0;
+    uint64_t afterCalls = 0;
+    rt.loop([&](std::string*) { return b++ < beforeTrue; }, [&](std::string*) { afterCalls++; return a++ < afterTrue; });
+    out[0] = rt.loopPasses(); out[1] = rt.framesPresented(); out[2] = afterCalls;
+}
+
+// a PNG byte stream -> top-down samples with `wantChannels` channels (0 = the file's), like stbi_load_from_memory(.., want)
+int evplp_host_png_info(const uint8_t* data, uint64_t n, int32_t* width, int32_t* height, int32_t* fileChannels) {
+    GUARD(png::Image img = png::Decode(data, (size_t)n, 0); *width = img.width; *height = img.height;
+          *fileChannels = img.fileChannels; return 0;)
+}
+int evplp_host_png_decode(const uint8_t* data, uint64_t n, int wantChannels, uint8_t* out, uint64_t capacity) {
+    GUARD(png::Image img = png::Decode(data, (size_t)n, wantChannels);
+          if (img.pixels.size() > capacity) throw std::runtime_error("evplp_host_png_decode: output buffer too small");
+          memcpy(out, img.pixels.data(), img.pixels.size()); return 0;)
 }
 int evplp_host_texture_load(const char* path, float gamma, int32_t* width, int32_t* height, float* rgbaOut, uint64_t capacityFloats) {
     GUARD(RtTexture t(std::string(path), gamma); *width = t.mWidth; *height = t.mHeight;

@@ -28,6 +28,7 @@
 #include "../../include/evplp.h"
 #include "json.h"
 #include "jpegdecode.h"
+#include "pngdecode.h"
 
 namespace evplp_host {
 
@@ -85,6 +86,18 @@ struct RtTexture {
             }
             mWidth = img.width; mHeight = img.height;
             rgb.swap(img.rgb);
+        } else if (png::IsPng(bytes.data(), bytes.size())) {
+            // stbi_load(.., 3): grey replicated, alpha dropped.  (The reference's own 4-channel branch then indexes this
+            // 3-channel buffer with stride 4, rtcommon.h:178-189 -- a bug no bundled scene reaches; here every file is read
+            // as the 3 channels stb returned.)
+            png::Image img;
+            try {
+                img = png::Decode(bytes.data(), bytes.size(), 3);
+            } catch (const std::exception& e) {
+                throw std::runtime_error("RtTexture: " + filepath + ": " + e.what());
+            }
+            mWidth = img.width; mHeight = img.height;
+            rgb.swap(img.pixels);
         } else {
             decodePnm(bytes, filepath, &rgb);
         }
@@ -115,7 +128,7 @@ private:
         };
         const std::string magic = bytes.size() >= 2 ? next_token() : std::string();
         if (magic != "P6" && magic != "P5")
-            throw std::runtime_error("RtTexture: " + filepath + " is neither JPEG nor binary PPM/PGM (the reference's scenes use JPEG only)");
+            throw std::runtime_error("RtTexture: " + filepath + " is not a JPEG, PNG or binary PPM/PGM file");
         mWidth = atoi(next_token().c_str()); mHeight = atoi(next_token().c_str());
         const int maxv = atoi(next_token().c_str());
         pos++;  // the single whitespace after maxval

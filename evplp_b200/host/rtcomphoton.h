@@ -13,6 +13,7 @@
 #include <iomanip>
 #include <random>
 #include "floatimage.h"
+#include "realtime.h"
 #include "rttechnique.h"
 
 namespace evplp_host {
@@ -359,11 +360,24 @@ public:
 
     // rtcomphoton.h:883-1133 (headless: RealTime::loop without the window)
     void run() {
-        while (iterate()) {
-            if (mDoWriteEveryFrame && mWorldSize == 1) writeFrame();
-        }
+        RealTime rt(mSink);
+        rt.loop([&](std::string*) { return iterate(); },          // before swap: one iteration, false = stop
+                [&](std::string* titleExtend) {                    // after swap (:1070-1104): progress title, writeEveryFrame
+                    if (mNumMaxIteration > 0) {
+                        const float iterRatio = (float)mNumIterations / (float)mNumMaxIteration;
+                        const float time = (float)mMasterWatch.timeMilliSec() / 1000.0f;
+                        const float etc = time / iterRatio - time;
+                        *titleExtend = std::to_string(iterRatio * 100.0f) + "%, ETC : " + std::to_string(etc) + "s";
+                    }
+                    if (mDoWriteEveryFrame && mWorldSize == 1) writeFrame();
+                    return true;
+                });
+        mLastTitle = rt.windowTitle();
+        mFramesPresented = rt.framesPresented();
         finish();
     }
+    // optional viewer / probe behind the headless loop (RealTime::Sink: present, shouldClose = ESC / window closed, title)
+    void setSink(RealTime::Sink* sink) { mSink = sink; }
 
     void reduce() {
         if (mWorldSize > 1 && mNcclComm) check(evplp_reduce(mHandle, mNcclComm), "evplp_reduce");
@@ -453,6 +467,9 @@ protected:
     std::unique_ptr<IndependentSampler> mMainSampler;
     int mNumIterations = 0;
     StopWatch mMasterWatch;
+    RealTime::Sink* mSink = nullptr;
+    std::string mLastTitle;
+    uint64_t mFramesPresented = 0;
     float mPrevTiming = 0, mElapsedMs = 0;
     FloatImage mCombined;
 };

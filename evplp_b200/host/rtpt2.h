@@ -38,7 +38,12 @@ public:
     void render(shared_ptr<RtScene>& scene, const Vec2& resolution, const Json& json) override {
         parse(scene, resolution, json);
         setup();
-        while (iterate()) {}
+        RealTime rt(mSink);   // rtpt2.h:608-692: the same loop contract; after swap = time limit (checked in iterate()) + writeEveryFrame
+        rt.loop([&](std::string*) { return iterate(); },
+                [&](std::string*) {
+                    if (mDoWriteEveryFrame && mWorldSize == 1) writeFrame();
+                    return true;
+                });
         finish();
         destroy();
     }
@@ -119,6 +124,22 @@ public:
         FloatImage::Save(FloatImage::FlipY(result), mOutputFilename);
     }
 
+    void writeFrame() {  // writeEveryFrame (rtpt2.h:669-689): <output>_<numIterations>.<ext>
+        check(evplp_synchronize(mHandle), "evplp_synchronize");
+        FloatImage result;
+        if (mFrameMode == ClearEveryFrame) {
+            result = runFinalProgram(1.0f, 1.0f, false);
+        } else {
+            FloatImage lightImage = runFinalProgram(0.0f, 1.0f, false);
+            FloatImage ptImage = runFinalProgram(1.0f, 0.0f, false);
+            ptImage *= 1.0f / (float)mNumIterations;
+            result = lightImage + ptImage;
+        }
+        const size_t i = mOutputFilename.find_last_of('.');
+        const std::string ext = i == std::string::npos ? std::string() : mOutputFilename.substr(i);
+        FloatImage::Save(FloatImage::FlipY(result), mOutputFilename.substr(0, i) + "_" + std::to_string(mNumIterations) + ext);
+    }
+
     void destroy() {
         if (mHandle) { evplp_destroy(mHandle); mHandle = nullptr; }
     }
@@ -132,6 +153,8 @@ public:
     float mTimelimitMs = 0;
     EFrame mFrameMode = Accumulate;
     bool mJitter = true, mUseStat = false, mDoWriteEveryFrame = false;
+    RealTime::Sink* mSink = nullptr;
+    void setSink(RealTime::Sink* sink) { mSink = sink; }
     std::string mOutputFilename, mStatFilename;
 
 private:

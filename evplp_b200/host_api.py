@@ -89,6 +89,10 @@ def load_host_library():
     lib.evplp_host_config_check.argtypes = [_P, C.c_char_p, C.POINTER(C.c_double)]
     lib.evplp_host_jpeg_info.argtypes = [_P, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.evplp_host_jpeg_decode.argtypes = [_P, C.c_uint64, _P, C.c_uint64]
+    lib.evplp_host_png_info.argtypes = [_P, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.evplp_host_png_decode.argtypes = [_P, C.c_uint64, C.c_int, _P, C.c_uint64]
+    lib.evplp_host_realtime_probe.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    lib.evplp_host_realtime_probe.restype = None
     lib.evplp_host_texture_load.argtypes = [C.c_char_p, C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.c_uint64]
     _lib = lib
     return lib
@@ -324,6 +328,38 @@ def decode_jpeg(data):
     if lib.evplp_host_jpeg_decode(buf, len(data), out.ctypes.data_as(_P), out.size) != 0:
         _err(lib, "evplp_host_jpeg_decode")
     return out, ch.value
+
+
+def decode_png(data, want_channels=0):
+    """PNG bytes -> (uint8 [H, W, C] top-down, file channel count): what stbi_load_from_memory(.., want_channels) returns."""
+    lib = load_host_library()
+    buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+    w, h, ch = C.c_int32(), C.c_int32(), C.c_int32()
+    if lib.evplp_host_png_info(buf, len(data), C.byref(w), C.byref(h), C.byref(ch)) != 0:
+        _err(lib, "evplp_host_png_info")
+    c = want_channels or ch.value
+    out = np.empty((h.value, w.value, c), dtype=np.uint8)
+    if lib.evplp_host_png_decode(buf, len(data), want_channels, out.ctypes.data_as(_P), out.size) != 0:
+        _err(lib, "evplp_host_png_decode")
+    return out, ch.value
+
+
+def realtime_probe(before_true, after_true, close_after=-1):
+    """(loop passes, frames presented, afterSwap calls) of the headless RealTime::loop for scripted callbacks."""
+    lib = load_host_library()
+    out = (C.c_uint64 * 3)()
+    lib.evplp_host_realtime_probe(before_true, after_true, close_after, out)
+    return tuple(out)
+
+
+def pfm_masked_error(a, b, mask_png, relative=True):
+    lib = load_host_library()
+    lib.evplp_host_pfm_masked_error.restype = C.c_float
+    lib.evplp_host_pfm_masked_error.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    v = lib.evplp_host_pfm_masked_error(a.encode(), b.encode(), mask_png.encode(), 1 if relative else 0)
+    if v < 0:
+        _err(lib, "evplp_host_pfm_masked_error")
+    return v
 
 
 def load_texture(path, gamma=1.0):

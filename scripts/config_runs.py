@@ -10,11 +10,11 @@ BASE = {"rngOffset": 0, "numMaxIteration": -1, "timeLimitMs": -1.0, "frameMode":
         "numMaxBounces": 3, "DoProgressive": True, "AlphaProgressive": 0.7}
 
 
-def run(name, scene, detail, W, H, iters, **kw):
+def run(name, scene, detail, W, H, iters, lvc=False, **kw):
     fam = dict(BASE); fam.update(kw)
     t0 = time.time()
     hs = HA.HostScene.generate(scene, 1, detail, W / H)
-    t = HA.Technique(hs, fam, W, H)
+    t = HA.Technique(hs, fam, W, H, lvc=lvc)
     h = t.device_handle()
     ms = C.c_float(); lib.evplp_last_stage_ms(h, capi.STAGE_BVH, C.byref(ms)); bvh = ms.value
     setup = time.time() - t0
@@ -44,3 +44,20 @@ if "C3" in which:
 if "C4" in which:
     run("C4 buddha ~1M tris 3840x2160 VPL gather (reduced: 256 VPL paths)", "buddha", 8, 3840, 2160, 1,
         numLightPaths=65536, numVplLightPaths=256, radiusPercentage=0.003, misMode="one")
+if "C3s" in which:   # profiling size: the VSL gather kernel with few enough VSLs that ncu's ~40 replays fit
+    run("C3 (profiling size) livingroom 1920x1080 VSL gather, 32 VPL paths", "livingroom", 8, 1920, 1080, 1,
+        numLightPaths=65536, numVplLightPaths=32, radiusPercentage=0.003, forceVsl=True, vslRadiusPercentage=0.05, misMode="one")
+if "LVC" in which:
+    run("LVC conference 1920x1080, per-pixel window of light paths", "conference", 8, 1920, 1080, 1, lvc=True,
+        numLightPaths=65536, numVplLightPaths=64, radiusPercentage=0.003, misMode="balance")
+if "PT" in which:
+    t0 = time.time()
+    hs = HA.HostScene.generate("conference", 1, 8, 1920 / 1080)
+    pt = HA.PathTracer(hs, {"rngOffset": 0, "numMaxIteration": -1, "timeLimitMs": -1.0, "frameMode": "accumulate", "outputFilename": "pt.pfm",
+                            "statFilename": "s.json", "useJitter": True, "useStat": False, "numSamplePerPixel": 1, "numMaxBounces": 3}, 1920, 1080)
+    for _ in range(2):
+        pt.iterate()
+    img = pt.final(0.5, 0.0)
+    print(json.dumps({"config": "RtPt2 conference 1920x1080, 2 iterations", "s": round(time.time() - t0, 2),
+                      "mean_rgb": [round(float(v), 4) for v in img.mean(axis=(0, 1))]}))
+    pt.close()
