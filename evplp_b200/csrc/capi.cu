@@ -91,6 +91,7 @@ int evplp_create(int device, int width, int height, evplp_handle* out) {
     CU(c->resolveOut.reserve(3 * n_px));
     CU(c->devStats.reserve(1));
     CU(c->skipMatrix.reserve(kSkipMatrixWords));
+    CU(c->skipTable.reserve(kSkipTableWords));
     CU(c->counters.reserve(4));
     CU(cudaMemsetAsync(c->devStats.p, 0, sizeof(DevStats), c->stream));
     CU(cudaMemsetAsync(c->accVpl.p, 0, sizeof(long long) * 3 * n_px, c->stream));
@@ -117,7 +118,7 @@ int evplp_destroy(evplp_handle c) {
     c->leafParent.release(); c->rangeFirst.release(); c->rangeLast.release(); c->nodeBounds.release();
     c->refitFlags.release(); c->nodes.release(); c->shaftNodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
     c->gatherCost.release(); c->gatherCostSorted.release(); c->gatherIota.release(); c->gatherOrder.release();
-    c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->records.release();
+    c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->skipTable.release(); c->records.release();
     c->vplList.release(); c->vplKeys.release(); c->vplKeysSorted.release(); c->vplVals.release(); c->vplOrder.release(); c->vplPrepared.release(); c->clusterBox.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
     c->accPhoton.release(); c->accLight.release(); c->accCount.release(); c->resolveOut.release(); c->devStats.release();
     if (c->resolvePinned) cudaFreeHost(c->resolvePinned);
@@ -245,7 +246,10 @@ static int ensure_skip_matrix(EvplpContext* c, uint32_t subsequence) {
     if (c->skipMatrixValid && c->skipMatrixSeed == subsequence) return EVPLP_OK;
     static thread_local uint32_t host[kSkipMatrixWords];
     xorwow_compose_skip(subsequence, host);
+    static thread_local uint32_t hostTab[kSkipTableWords];
+    xorwow_build_tables(host, hostTab);
     CU(cudaMemcpyAsync(c->skipMatrix.p, host, sizeof(host), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->skipTable.p, hostTab, sizeof(hostTab), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));  // `host` is reused by the next call
     c->skipMatrixSeed = subsequence;
     c->skipMatrixValid = true;

@@ -99,6 +99,7 @@ struct EvplpContext {
     EvplpParams params;
     bool paramsSet = false;
     evplp::DevBuf<uint32_t> skipMatrix;           // 800 words: composed XORWOW skip matrix
+    evplp::DevBuf<uint32_t> skipTable;            // kSkipTableWords: the same matrix as 4-bit look-up tables (light tracing)
     uint32_t skipMatrixSeed = 0xffffffffu;
     bool skipMatrixValid = false;
 

@@ -51,3 +51,19 @@ void xorwow_compose_skip(uint32_t subsequence, uint32_t* out800) {
 }
 
 }  // namespace evplp
+
+// Host-only self-check of the table form (xorwow_seed_skip) against the matrix form (xorwow_seed + xorwow_apply_matrix):
+// returns the number of seeds in [firstSeed, firstSeed + numSeeds) whose states differ.  No device is touched.
+extern "C" int evplp_debug_xorwow_tables(uint32_t subsequence, uint32_t firstSeed, uint32_t numSeeds) {
+    static thread_local uint32_t m[evplp::kSkipMatrixWords], tab[evplp::kSkipTableWords];
+    evplp::xorwow_compose_skip(subsequence, m);
+    evplp::xorwow_build_tables(m, tab);
+    int bad = 0;
+    for (uint32_t k = 0; k < numSeeds; k++) {
+        evplp::Xorwow a = evplp::xorwow_seed(firstSeed + k);
+        evplp::xorwow_apply_matrix(a, m);
+        const evplp::Xorwow b = evplp::xorwow_seed_skip(firstSeed + k, tab);
+        if (a.v0 != b.v0 || a.v1 != b.v1 || a.v2 != b.v2 || a.v3 != b.v3 || a.v4 != b.v4 || a.d != b.d) bad++;
+    }
+    return bad;
+}

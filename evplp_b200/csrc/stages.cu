@@ -140,16 +140,16 @@ __device__ __forceinline__ V3 light_sample(const DevScene& sc, V3* position, V3*
 __global__ void __launch_bounds__(128, 8) light_trace_kernel(DevScene sc, const uint32_t* __restrict__ skip,
                                                           EvplpRecord* __restrict__ records, uint32_t firstPath,
                                                           uint32_t numPaths, uint32_t B1, DevStats* stats) {
-    __shared__ uint32_t sm[kSkipMatrixWords];
-    for (int k = threadIdx.x; k < kSkipMatrixWords; k += blockDim.x) sm[k] = skip[k];
+    __shared__ __align__(16) uint32_t sm[kSkipTableWords];   // `skip` = the launch's skip matrix as 4-bit tables (xorwow.h)
+    for (int k = threadIdx.x; k < kSkipTableWords / 4; k += blockDim.x)
+        reinterpret_cast<uint4*>(sm)[k] = __ldg(reinterpret_cast<const uint4*>(skip) + k);
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numPaths) return;
     EvplpRecord* rec = records + (size_t)i * B1;
 
     // curand_init(launchId, rngSeed, 0) -- lighttracing.cu:203
-    Xorwow rng = xorwow_seed(firstPath + i);
-    xorwow_apply_matrix(rng, sm);
+    Xorwow rng = xorwow_seed_skip(firstPath + i, sm);
 
     V3 position, normal;
     V3 flux = light_sample(sc, &position, &normal, rng);
@@ -934,8 +934,15 @@ __global__ void __launch_bounds__(256) splat_tile_kernel(SplatParams sp, TileGri
     const bool valid = inside && gprim[i] >= 0;
     const V3 w10 = normalize(sp.U.cameraPosition - sf.pos);
     const float r2 = sp.U.radius * sp.U.radius;
+    const float r2Cull = r2 * 1.001f;
     const float invR2 = det_div(1.0f, sp.U.radius * sp.U.radius);
     const float invN = det_div(1.0f, (float)sp.U.numLightPaths);
+    // box of the surface points of this warp's sub-block (empty when no texel of it is valid: then nothing survives the cull)
+    V3 blo = valid ? sf.pos : v3s(INFINITY), bhi = valid ? sf.pos : v3s(-INFINITY);
+    for (int o = 16; o > 0; o >>= 1) {
+        blo = v3(fminf(blo.x, __shfl_xor_sync(0xffffffffu, blo.x, o)), fminf(blo.y, __shfl_xor_sync(0xffffffffu, blo.y, o)), fminf(blo.z, __shfl_xor_sync(0xffffffffu, blo.z, o)));
+        bhi = v3(fmaxf(bhi.x, __shfl_xor_sync(0xffffffffu, bhi.x, o)), fmaxf(bhi.y, __shfl_xor_sync(0xffffffffu, bhi.y, o)), fmaxf(bhi.z, __shfl_xor_sync(0xffffffffu, bhi.z, o)));
+    }
     long long a0 = 0, a1 = 0, a2 = 0;
     unsigned frags = 0;
     for (uint32_t base = begin; base < end; base += SPLAT_BATCH) {
@@ -944,14 +951,29 @@ __global__ void __launch_bounds__(256) splat_tile_kernel(SplatParams sp, TileGri
         for (uint32_t k = threadIdx.x; k < nb * SPLAT_PREP_F4; k += blockDim.x)
             batch[k] = __ldg(prep + (size_t)tileList[first + base + k / SPLAT_PREP_F4] * SPLAT_PREP_F4 + k % SPLAT_PREP_F4);
         __syncthreads();
-        // phase 1: radius test of this texel against every staged photon -> 64-bit hit mask (cheap, uniform loop)
-        unsigned long long hits = 0ull;
-        if (valid) {
-            for (uint32_t j = 0; j < nb; j++) {
+        // phase 0: which staged photons can touch this warp's 8x4-texel sub-block at all?  Lane l tests photons l and l + 32
+        // against the box of the sub-block's surface points (sphere vs. box, with a margin far above the rounding of the exact
+        // test below, so the cull never changes a decision); a photon's footprint covers a few of the tile's eight sub-blocks.
+        unsigned long long cand = 0ull;
+#pragma unroll
+        for (int h = 0; h < SPLAT_BATCH / 32; h++) {
+            const uint32_t j = (uint32_t)(lane + 32 * h);
+            bool keep = false;
+            if (j < nb) {
                 const float4 p0 = batch[j * SPLAT_PREP_F4];
-                const V3 d = v3(p0.x, p0.y, p0.z) - sf.pos;
-                if (!(dot(d, d) > r2)) hits |= 1ull << j;
+                const float dx = fmaxf(fmaxf(blo.x - p0.x, p0.x - bhi.x), 0.0f), dy = fmaxf(fmaxf(blo.y - p0.y, p0.y - bhi.y), 0.0f),
+                            dz = fmaxf(fmaxf(blo.z - p0.z, p0.z - bhi.z), 0.0f);
+                keep = !(dx * dx + dy * dy + dz * dz > r2Cull);
             }
+            cand |= (unsigned long long)__ballot_sync(0xffffffffu, keep) << (32 * h);
+        }
+        // phase 1: exact radius test of this texel against the surviving photons -> 64-bit hit mask (warp-uniform loop)
+        unsigned long long hits = 0ull;
+        for (unsigned long long cm = cand; cm; cm &= cm - 1ull) {
+            const int j = __ffsll((long long)cm) - 1;
+            const float4 p0 = batch[j * SPLAT_PREP_F4];
+            const V3 d = v3(p0.x, p0.y, p0.z) - sf.pos;
+            if (valid && !(dot(d, d) > r2)) hits |= 1ull << j;
         }
         // phase 2: every lane shades ITS OWN hits (ascending j), so a warp iterates max-hits-per-lane times instead of
         // once per photon that any of its lanes touches
@@ -983,11 +1005,15 @@ __global__ void __launch_bounds__(256) splat_tile_kernel(SplatParams sp, TileGri
     }
 }
 
-__global__ void tile_summary_kernel(const uint32_t* __restrict__ tileCount, int numTiles, uint32_t* __restrict__ out /* [0] max */) {
+// out[0] = largest per-tile count; total = sum of the counts in 64 bits (the 32-bit scan wraps beyond 2^32 entries: the caller
+// compares THIS total with the capacity before it trusts the offsets)
+__global__ void tile_summary_kernel(const uint32_t* __restrict__ tileCount, int numTiles, uint32_t* __restrict__ out /* [0] max */,
+                                    unsigned long long* __restrict__ total) {
     uint32_t m = 0;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < numTiles; t += gridDim.x * blockDim.x) m = max(m, tileCount[t]);
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+    unsigned long long sum = 0ull;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < numTiles; t += gridDim.x * blockDim.x) { m = max(m, tileCount[t]); sum += tileCount[t]; }
+    for (int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+    if ((threadIdx.x & 31) == 0 && m) { atomicMax(out, m); atomicAdd(total, sum); }
 }
 
 // ------------------------------------------------------------------ light / resolve -----
@@ -1043,6 +1069,7 @@ struct FlagPred {
 
 static cudaError_t compact_records(EvplpContext* c, uint64_t first, uint64_t count, uint32_t mask, DevBuf<uint32_t>& list,
                                    uint32_t* devCount) {
+    if (count > 0x7fffffffull || first + count > 0xffffffffull) return cudaErrorInvalidValue;   // 32-bit record indices, int num_items of cub
     cudaError_t e = list.reserve(count ? count : 1);
     if (e != cudaSuccess) return e;
     thrust::counting_iterator<uint32_t> it((uint32_t)first);
@@ -1078,7 +1105,7 @@ cudaError_t launch_light_trace(EvplpContext* c, uint32_t rngSeed, uint32_t first
     if (numPaths == 0) return cudaSuccess;
     const uint32_t B1 = c->params.numPhotonsPerLightPath;
     c->stageBegin(ST_LIGHT_TRACE);
-    light_trace_kernel<<<(numPaths + 127) / 128, 128, 0, c->stream>>>(c->scene(), c->skipMatrix.p, c->records.p, firstPath,
+    light_trace_kernel<<<(numPaths + 127) / 128, 128, 0, c->stream>>>(c->scene(), c->skipTable.p, c->records.p, firstPath,
                                                                       numPaths, B1, c->devStats.p);
     c->stageEnd(ST_LIGHT_TRACE);
     c->launches++;
@@ -1281,9 +1308,9 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
         e = c->splatPrep.reserve((size_t)count * SPLAT_PREP_F4); if (e != cudaSuccess) return e;
         e = c->tileCount.reserve((size_t)numTiles + 1); if (e != cudaSuccess) return e;
         e = c->tileOffset.reserve((size_t)numTiles + 1); if (e != cudaSuccess) return e;
-        e = c->tileCursor.reserve((size_t)numTiles + 2); if (e != cudaSuccess) return e;
+        e = c->tileCursor.reserve((size_t)numTiles + 6); if (e != cudaSuccess) return e;
         e = cudaMemsetAsync(c->tileCount.p, 0, sizeof(uint32_t) * (numTiles + 1), c->stream); if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(c->tileCursor.p, 0, sizeof(uint32_t) * (numTiles + 2), c->stream); if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(c->tileCursor.p, 0, sizeof(uint32_t) * (numTiles + 6), c->stream); if (e != cudaSuccess) return e;
         c->stageBegin(ST_SPLAT);
         const unsigned pb = (count + 255) / 256;
         splat_prepare_kernel<<<pb, 256, 0, c->stream>>>(sp, tg, c->records.p, c->photonList.p, devCount, c->splatPrep.p, c->tileCount.p);
@@ -1292,15 +1319,17 @@ cudaError_t launch_splat(EvplpContext* c, uint64_t firstRecord, uint64_t numReco
         e = c->sortTemp.reserve(tempBytes); if (e != cudaSuccess) return e;
         e = cub::DeviceScan::ExclusiveSum(c->sortTemp.p, tempBytes, c->tileCount.p, c->tileOffset.p, numTiles + 1, c->stream); if (e != cudaSuccess) return e;
         uint32_t* summary = c->tileCursor.p + numTiles + 1;  // max photons per tile
-        tile_summary_kernel<<<32, 256, 0, c->stream>>>(c->tileCount.p, numTiles, summary);
+        unsigned long long* total64 = reinterpret_cast<unsigned long long*>(c->tileCursor.p + (((size_t)numTiles + 3) & ~(size_t)1));  // 8-byte aligned slot
+        tile_summary_kernel<<<32, 256, 0, c->stream>>>(c->tileCount.p, numTiles, summary, total64);
         c->launches += 4;
-        uint32_t totalEntries = 0, maxPerTile = 0;
-        e = cudaMemcpyAsync(&totalEntries, c->tileOffset.p + numTiles, 4, cudaMemcpyDeviceToHost, c->stream); if (e != cudaSuccess) return e;
+        unsigned long long totalEntries = 0;   // 64-bit: the 32-bit offsets are only trusted when this fits the capacity below
+        uint32_t maxPerTile = 0;
+        e = cudaMemcpyAsync(&totalEntries, total64, 8, cudaMemcpyDeviceToHost, c->stream); if (e != cudaSuccess) return e;
         e = cudaMemcpyAsync(&maxPerTile, summary, 4, cudaMemcpyDeviceToHost, c->stream); if (e != cudaSuccess) return e;
         e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) return e;
         if (totalEntries == 0) { c->stageEnd(ST_SPLAT); return cudaSuccess; }
-        if ((uint64_t)totalEntries <= (uint64_t)c->opt.splatMaxEntries) {
-            e = c->tileList.reserve(totalEntries); if (e != cudaSuccess) return e;
+        if ((uint64_t)totalEntries <= (uint64_t)c->opt.splatMaxEntries && totalEntries <= 0xffffffffull) {
+            e = c->tileList.reserve((size_t)totalEntries); if (e != cudaSuccess) return e;
             splat_fill_kernel<<<pb, 256, 0, c->stream>>>(sp, tg, c->splatPrep.p, devCount, c->tileOffset.p, c->tileCursor.p, c->tileList.p);
             const unsigned chunks = (maxPerTile + SPLAT_CHUNK - 1) / SPLAT_CHUNK;
             dim3 grid(tg.nx, tg.ny, chunks);

@@ -62,6 +62,63 @@ EVPLP_HD void xorwow_apply_matrix(Xorwow& s, const uint32_t* m) {
     s.v0 = r0; s.v1 = r1; s.v2 = r2; s.v3 = r3; s.v4 = r4;
 }
 
+// ---- the same mat-vec through 4-bit tables --------------------------------------------------------------------------
+// Of the seeded state only v0, v1, v4 depend on the seed (xorwow_seed: v2, v3 come from the constant high seed word), so
+// state * M = K ^ rows selected by the 96 varying bits, K = the contribution of the constant words.  The host folds the
+// matrix into 24 tables (one per nibble of v0, v1, v4) of 16 entries x 5 words (padded to 8): 24 look-ups of 32 bytes
+// replace 160 row selections (~240 instead of ~2000 instructions per path).  K is folded into table 0 (exactly one of
+// its entries is always selected).  Layout: tab[((w * 8 + nibble) * 16 + value) * 8 + k], w = 0, 1, 2 for v0, v1, v4.
+constexpr int kSkipTableWords = 24 * 16 * 8;
+
+inline void xorwow_build_tables(const uint32_t* m /* 800 words */, uint32_t* tab /* kSkipTableWords */) {
+    const Xorwow z = xorwow_seed(0u);   // v2, v3 do not depend on the seed
+    uint32_t K[5] = {0, 0, 0, 0, 0};
+    const uint32_t cw[2] = {z.v2, z.v3};
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 32; j++)
+            if ((cw[i] >> j) & 1u)
+                for (int k = 0; k < 5; k++) K[k] ^= m[5 * ((2 + i) * 32 + j) + k];
+    const int wordOf[3] = {0, 1, 4};
+    for (int w = 0; w < 3; w++)
+        for (int n = 0; n < 8; n++)
+            for (int x = 0; x < 16; x++) {
+                uint32_t* e = tab + ((w * 8 + n) * 16 + x) * 8;
+                for (int k = 0; k < 8; k++) e[k] = 0u;
+                for (int b = 0; b < 4; b++)
+                    if ((x >> b) & 1)
+                        for (int k = 0; k < 5; k++) e[k] ^= m[5 * (wordOf[w] * 32 + 4 * n + b) + k];
+                if (w == 0 && n == 0)
+                    for (int k = 0; k < 5; k++) e[k] ^= K[k];
+            }
+}
+
+// xorwow_seed(seed) followed by xorwow_apply_matrix, through the tables (bit-identical)
+EVPLP_HD Xorwow xorwow_seed_skip(uint32_t seed, const uint32_t* tab) {
+    Xorwow s = xorwow_seed(seed);
+    const uint32_t in[3] = {s.v0, s.v1, s.v4};
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 0; w < 3; w++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int n = 0; n < 8; n++) {
+            const uint32_t x = (in[w] >> (4 * n)) & 15u;
+            const uint32_t* e = tab + ((w * 8 + n) * 16 + x) * 8;
+#if defined(__CUDA_ARCH__)
+            const uint4 a = *reinterpret_cast<const uint4*>(e);
+            r0 ^= a.x; r1 ^= a.y; r2 ^= a.z; r3 ^= a.w; r4 ^= e[4];
+#else
+            r0 ^= e[0]; r1 ^= e[1]; r2 ^= e[2]; r3 ^= e[3]; r4 ^= e[4];
+#endif
+        }
+    }
+    s.v0 = r0; s.v1 = r1; s.v2 = r2; s.v3 = r3; s.v4 = r4;
+    return s;
+}
+
 EVPLP_HD uint32_t xorwow_next(Xorwow& s) {
     uint32_t t = s.v0 ^ (s.v0 >> 2);
     s.v0 = s.v1;

@@ -242,6 +242,9 @@ int evplp_debug_uniforms(evplp_handle h, uint32_t seed, uint32_t subsequence, ui
  * (curand_init(seed, subsequence, 0, &state); curand_uniform(&state) -- lighttracing.cu:202-203).
  * Pins the XORWOW restatements (product and oracle) against cuRAND itself. */
 int evplp_debug_curand(evplp_handle h, uint32_t seed, uint32_t subsequence, uint32_t n, float* out);
+/* Host-only self-check: the 4-bit-table form of the per-launch XORWOW skip (what light tracing uses) against the 160x160
+ * matrix form, over numSeeds launch indices; returns the number of differing states (0 expected).  No device needed. */
+int evplp_debug_xorwow_tables(uint32_t subsequence, uint32_t firstSeed, uint32_t numSeeds);
 /* detmath on device: op 0 sin, 1 cos, 2 pow(x,y), 3 asin, 4 sqrt; x,y,out are n floats */
 int evplp_debug_math(evplp_handle h, int op, const float* x, const float* y, uint32_t n, float* out);
 int evplp_stats(evplp_handle h, EvplpStats* stats);
