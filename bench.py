@@ -198,7 +198,10 @@ def run_gpu(args):
         name, value = kv.split("=")
         capi.check(lib, lib.evplp_set_option(None, name.encode(), int(value)), "set_option")
     hs = HA.HostScene.generate(SCENE, SEED, DETAIL, RES_X / RES_Y)
-    tech = HA.Technique(hs, PHOTONFAM, RES_X, RES_Y, device=local_rank, rank=rank, world_size=world)
+    if args.tile_share > 1:   # profiling only: this process gathers every Nth 8x4-pixel tile of the headline frame
+        tech = HA.Technique(hs, PHOTONFAM, RES_X, RES_Y, device=local_rank, rank=0, world_size=args.tile_share, image_partition=True)
+    else:
+        tech = HA.Technique(hs, PHOTONFAM, RES_X, RES_Y, device=local_rank, rank=rank, world_size=world)
     h = tech.device_handle()
 
     def ck(rc, what):
@@ -445,7 +448,7 @@ def run_gpu(args):
             if dbg[6]:
                 line["cluster_gather"] = {"descents_per_step": dbg[6] / dbg[0], "candidate_batches_per_descent": dbg[7] / dbg[6],
                                           "candidates_per_descent": dbg[3] / dbg[6], "packet_steps_frac": dbg[1] / dbg[0]}
-                if os.environ.get("EVPLP_LIB"):   # tuning build (-DEVPLP_GATHER_PROF): warp-cycles per region of the item loop
+                if "prof" in os.environ.get("EVPLP_LIB", ""):   # tuning build (-DEVPLP_GATHER_PROF): warp-cycles per region of the item loop
                     line["cluster_gather"]["prof_cycles_stage_clusterdescent_sharedtests_vpldescent_vpltests_packet_shading_setup"] = [
                         int(hist[k]) for k in (1, 2, 3, 4, 5, 6, 7, 8)]
                 elif any(hist):   # tuning build (-DEVPLP_GATHER_HIST)
@@ -490,6 +493,7 @@ def main():
     ap.add_argument("--vpl-paths", type=int, default=None, help="override numVplLightPaths (profiling only)")
     ap.add_argument("--light-paths", type=int, default=None, help="override numLightPaths (profiling only)")
     ap.add_argument("--res", default=None, help="override WxH (profiling only)")
+    ap.add_argument("--tile-share", type=int, default=1, help="profiling only: gather every Nth 8x4-pixel tile of the frame (image partition, rank 0 of N)")
     ap.add_argument("--opt", action="append", default=[], help="evplp_set_option name=value (tuning experiments)")
     args = ap.parse_args()
     global RES_X, RES_Y, WORKLOAD
@@ -499,9 +503,9 @@ def main():
         PHOTONFAM["numLightPaths"] = args.light_paths
     if args.res:
         RES_X, RES_Y = (int(v) for v in args.res.lower().split("x"))
-    if args.vpl_paths is not None or args.light_paths is not None or args.res:
+    if args.vpl_paths is not None or args.light_paths is not None or args.res or args.tile_share > 1:
         WORKLOAD = (f"NON-HEADLINE profiling override: {RES_X}x{RES_Y}, numVplLightPaths={PHOTONFAM['numVplLightPaths']}, "
-                    f"numLightPaths={PHOTONFAM['numLightPaths']}; " + WORKLOAD)
+                    f"numLightPaths={PHOTONFAM['numLightPaths']}, every {args.tile_share}th tile; " + WORKLOAD)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -45,6 +45,7 @@ struct Options {
     int gatherMode = 1;          // 1 = shaft traversal of the 32-wide hierarchy, 0 = per-ray packet traversal, 2 = shaft in VSL too
     int gatherAlgo = 1;          // 1 = VPL-cluster gather (tolerance mode, default), 0 = per-VPL exact-order gather
     int clusterSize = 16;        // VPLs per cluster of the cluster gather
+    int sharedBatches = 3, vplBatches = 3, clusterSkipMax = 64;   // cluster gather: candidate batches a shared / a per-VPL descent may stream; longest run of clusters that skip the shared attempt after a fat shaft
     int shaftCandMax = 128, shaftStreak = 3, shaftSkip = 256;
     int gatherLpt = 1, gatherPersistent = 1;
     int splatGroup = 0, splatMode = 0;
@@ -121,6 +122,7 @@ struct EvplpContext {
 
     evplp::DevBuf<long long> accVpl, accPhoton;   // Q31.32, W*H*3
     evplp::DevBuf<uint32_t> accLight;             // W*H
+    evplp::DevBuf<unsigned long long> scratch64;  // small device scratch of the diagnostic taps (evplp_stats: emitted counts)
     evplp::DevBuf<long long> accCount;            // [0] iterations accumulated into the layers (reduced with them)
     float lightBoxMin[3] = {0, 0, 0}, lightBoxMax[3] = {0, 0, 0};   // world bounds of the light mesh (light pass rectangle)
     evplp::DevBuf<float> resolveOut;              // W*H*3

@@ -107,7 +107,7 @@ __device__ __forceinline__ V3 cross_rn(V3 a, V3 b) {
 }
 __device__ __forceinline__ bool tri_test(V3 org, V3 dir, float tmin, float tmax, V3 p0, V3 e0, V3 e1, V3 n,
                                          float* t, float* beta, float* gamma) {
-    const float inv = __fdiv_rn(1.0f, dot_rn(n, dir));
+    const float inv = __frcp_rn(dot_rn(n, dir));   // = 1.0f / x correctly rounded (what the oracle's division gives), without the general divide
     const V3 e2 = v3(__fmul_rn(inv, __fsub_rn(p0.x, org.x)), __fmul_rn(inv, __fsub_rn(p0.y, org.y)), __fmul_rn(inv, __fsub_rn(p0.z, org.z)));
     const V3 i = cross_rn(dir, e2);
     *beta = dot_rn(i, e1);
@@ -224,8 +224,37 @@ __device__ inline RayHit trace_closest(const DevScene& sc, V3 org, V3 dir, float
     float stackT[BVH_STACK];
     int sp = 0;
     uint32_t cur = 0;  // root node
-    while (true) {
-        if (cur & BVH_LEAF_BIT) {
+    // "while-while" order: a lane walks inner nodes until it holds a leaf (or runs out of work), and only then do the lanes of the
+    // warp test triangles together.  With an if / else per step, a warp whose lanes sit in different states pays for a node visit
+    // AND a leaf visit in every step; light paths are incoherent, so that is the common case.  The set of tests a ray performs is
+    // still a superset of what decides its closest hit (entries beyond the best hit are skipped), and every test is exact, so the
+    // result does not depend on the order.
+    for (;;) {
+        while (cur != BVH_EMPTY && !(cur & BVH_LEAF_BIT)) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
+            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+            const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+            float t0 = slab_entry_masked(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, bestT);
+            float t1 = slab_entry_masked(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, bestT);
+            float t2 = slab_entry_masked(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, bestT);
+            float t3 = slab_entry_masked(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, bestT);
+            uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+            cswap_desc(t0, c0, t1, c1); cswap_desc(t2, c2, t3, c3); cswap_desc(t0, c0, t2, c2);
+            cswap_desc(t1, c1, t3, c3); cswap_desc(t1, c1, t2, c2);
+            // (t0 >= t1 >= t2 >= t3; misses are +inf and sort to the front)
+            if (sp + 3 > BVH_STACK) { *overflow = 1; return best; }
+            if (t0 < INFINITY) { stack[sp] = c0; stackT[sp] = t0; sp++; }
+            if (t1 < INFINITY) { stack[sp] = c1; stackT[sp] = t1; sp++; }
+            if (t2 < INFINITY) { stack[sp] = c2; stackT[sp] = t2; sp++; }
+            cur = t3 < INFINITY ? c3 : BVH_EMPTY;  // nearest child continues without a stack round trip
+            while (cur == BVH_EMPTY && sp > 0) {
+                --sp;
+                if (stackT[sp] <= bestT) cur = stack[sp];  // entries that begin beyond the best hit cannot improve it (ties kept)
+            }
+        }
+        if (cur == BVH_EMPTY) return best;
+        {
             const uint32_t first = bvh_leaf_first(cur), count = bvh_leaf_count(cur);
             for (uint32_t k = 0; k < count; k++) {
                 const float4* tp = sc.triLeaf + 4 * (size_t)(first + k);
@@ -241,29 +270,10 @@ __device__ inline RayHit trace_closest(const DevScene& sc, V3 org, V3 dir, float
                 }
             }
             cur = BVH_EMPTY;
-        } else {
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-            const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
-            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
-            const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
-            float t0 = slab_entry_masked(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, bestT);
-            float t1 = slab_entry_masked(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, bestT);
-            float t2 = slab_entry_masked(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, bestT);
-            float t3 = slab_entry_masked(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, bestT);
-            uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
-            cswap_desc(t0, c0, t1, c1); cswap_desc(t2, c2, t3, c3); cswap_desc(t0, c0, t2, c2);
-            cswap_desc(t1, c1, t3, c3); cswap_desc(t1, c1, t2, c2);
-            // (t0 >= t1 >= t2 >= t3; misses are +inf and sort to the front)
-            if (sp + 3 > BVH_STACK) { *overflow = 1; break; }
-            if (t0 < INFINITY) { stack[sp] = c0; stackT[sp] = t0; sp++; }
-            if (t1 < INFINITY) { stack[sp] = c1; stackT[sp] = t1; sp++; }
-            if (t2 < INFINITY) { stack[sp] = c2; stackT[sp] = t2; sp++; }
-            cur = t3 < INFINITY ? c3 : BVH_EMPTY;  // nearest child continues without a stack round trip
-        }
-        while (cur == BVH_EMPTY) {
-            if (sp == 0) return best;
-            --sp;
-            if (stackT[sp] <= bestT) cur = stack[sp];  // entries that begin beyond the best hit cannot improve it (ties kept)
+            while (cur == BVH_EMPTY && sp > 0) {
+                --sp;
+                if (stackT[sp] <= bestT) cur = stack[sp];
+            }
         }
     }
     return best;

@@ -23,8 +23,8 @@ namespace evplp {
 constexpr int FG_CL_MAX = 16;      // staging capacity: VPLs per cluster
 constexpr int FG_PV = 6;           // float4 per prepared VPL
 constexpr int FG_CAND = 96;        // candidate leaves per batch of a descent (a node adds up to 32)
-constexpr int FG_SHARED_BATCHES = 3;   // a cluster's shared descent streams at most this many candidate batches; then its undecided rays go per VPL
-constexpr int FG_MAX_BATCHES = 3;  // a single VPL streams at most this many candidate batches before it switches to the packet traversal
+// (run-time knobs, FastParams: sharedBatches = candidate batches a cluster's shared descent may stream before its undecided rays go
+//  per VPL; vplBatches = batches a single VPL streams before it switches to the packet traversal; skipMax)
 constexpr int FG_SPLIT_ROUNDS = 3;  // depth groups per tile: up to 2^rounds
 constexpr float FG_SPLIT_RATIO = 2.5f;   // a group is cut while its distance range exceeds this many tile widths
 constexpr int FG_STACK = 96;       // inner-node stack of the descent (also the packet fallback's stack)
@@ -40,6 +40,7 @@ struct FastParams {
     uint32_t stride, offset;
     uint32_t numChunks;             // the cluster list is cut into numChunks ranges; work item = (tile, range)
     float tileAngle;                // width of an 8-pixel tile per unit of distance from the camera
+    int sharedBatches, vplBatches, skipMax;
 };
 
 // ---- fast math of the shading tail ---------------------------------------------------------------------------------
@@ -255,25 +256,39 @@ __device__ __forceinline__ bool test_batch(const DevScene& sc, uint32_t candBase
             km = cn - c0 >= 32 ? 0xffffffffu : ((1u << (cn - c0)) - 1u);
         }
         if (km && !haveSlab) { rs = make_slab_masked(org, dir); haveSlab = true; }
+        // phase 1: per-ray slab test of every surviving leaf box -> this lane's own list (bit q - c0)
+        unsigned mine = 0u;
         while (km) {
-            const int q = c0 + __ffs((int)km) - 1;
+            const int b = __ffs((int)km) - 1;
             km &= km - 1u;
-            const uint32_t qa = candBase + 4u * (uint32_t)q;
-            const bool inBox = active && !occ &&
-                               slab_masked(rs, ld_shared_f32(qa), ld_shared_f32(qa + 4u * FG_CAND), ld_shared_f32(qa + 8u * FG_CAND),
+            const uint32_t qa = candBase + 4u * (uint32_t)(c0 + b);
+            const bool inBox = slab_masked(rs, ld_shared_f32(qa), ld_shared_f32(qa + 4u * FG_CAND), ld_shared_f32(qa + 8u * FG_CAND),
                                            ld_shared_f32(qa + 12u * FG_CAND), ld_shared_f32(qa + 16u * FG_CAND),
                                            ld_shared_f32(qa + 20u * FG_CAND), tmin, tmax);
-            if (!__any_sync(full, inBox)) continue;
-            const uint32_t w = ld_shared_u32(qa + 24u * FG_CAND);
-            const uint32_t tfirst = bvh_leaf_first(w), tcount = bvh_leaf_count(w);
-            const float4* tp = sc.triLeaf + 4 * (size_t)tfirst;
-            for (uint32_t u = 0; u < tcount; u++, tp += 4) {
-                const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2), td = __ldg(tp + 3);
-                float tt, be, ga;
-                occ |= tri_test(org, dir, tmin, tmax, ld3(ta), ld3(tb), ld3(tc), ld3(td), &tt, &be, &ga);
-            }
-            if (!__any_sync(full, active && !occ)) return occ;
+            if (inBox) mine |= 1u << b;
         }
+        if (!active || occ) mine = 0u;
+        // phase 2: every lane runs the exact triangle tests of ITS OWN boxes, so the warp iterates max-boxes-per-ray times
+        // instead of once per leaf that any of its rays meets (near misses dominate: most boxes are met by a few rays only)
+        while (__any_sync(full, mine != 0u)) {
+            uint32_t tfirst = 0u, tcount = 0u;
+            if (mine) {
+                const int b = __ffs((int)mine) - 1;
+                mine &= mine - 1u;
+                const uint32_t w = ld_shared_u32(candBase + 4u * (uint32_t)(c0 + b) + 24u * FG_CAND);
+                tfirst = bvh_leaf_first(w); tcount = bvh_leaf_count(w);
+            }
+            for (uint32_t u = 0; __any_sync(full, u < tcount); u++) {
+                if (u < tcount) {
+                    const float4* tp = sc.triLeaf + 4 * (size_t)(tfirst + u);
+                    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2), td = __ldg(tp + 3);
+                    float tt, be, ga;
+                    occ |= tri_test(org, dir, tmin, tmax, ld3(ta), ld3(tb), ld3(tc), ld3(td), &tt, &be, &ga);
+                }
+            }
+            if (occ) mine = 0u;
+        }
+        if (!__any_sync(full, active && !occ)) return occ;
     }
     return occ;
 }
@@ -441,11 +456,11 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
                         }
                         FG_PROF_END(3);
                     }
-                    if (!done && ++batchNo >= FG_SHARED_BATCHES) break;   // a fat shaft: the occlusions found so far stand, the rest per VPL
+                    if (!done && ++batchNo >= fp.sharedBatches) break;   // a fat shaft: the occlusions found so far stand, the rest per VPL
                 }
                 if (!done) {
                     shared = false;
-                    skipLen = skipLen ? min(64, skipLen * 2) : 1;
+                    skipLen = skipLen ? min(fp.skipMax, skipLen * 2) : min(fp.skipMax, 1);
                     skipLeft = skipLen;
                     splits++;
                 } else {
@@ -482,7 +497,7 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
                             FG_PROF_END(5);
                             if (!__any_sync(full, active && !occ)) break;                  // every ray has its answer
                         }
-                        if (!done && ++batchNo >= FG_MAX_BATCHES) { usePacket = true; break; }   // far too many leaves: finish per ray
+                        if (!done && ++batchNo >= fp.vplBatches) { usePacket = true; break; }   // far too many leaves: finish per ray
                     }
                     FG_PROF_END(4);
                     if (usePacket) {
@@ -627,7 +642,7 @@ cudaError_t launch_debug_fast_pow(EvplpContext* c, const float* x, const float* 
 
 template <int MC>
 static void launch_mc(EvplpContext* c, dim3 grid, const FastParams& fp, uint32_t* tileCounter, const uint32_t* tileOrder, uint32_t* tileCost) {
-    const int mb = c->opt.gatherMinBlocks ? c->opt.gatherMinBlocks : 3;
+    const int mb = c->opt.gatherMinBlocks ? c->opt.gatherMinBlocks : 4;   // 64 registers, 32 warps / SM: the kernel is latency bound (measured: 4 > 3 > 2)
     if (mb >= 4)
         gather_cluster_kernel<MC, 4><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(c->scene(), fp, c->gbuf.p, c->vplPrepared.p, c->clusterBox.p, c->accVpl.p, c->devStats.p, tileCounter, tileOrder, tileCost);
     else if (mb == 2)
@@ -649,6 +664,7 @@ cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile t, GatherParams g, 
     const TileShare share = tile_share(c, t);
     fp.stride = share.stride; fp.offset = share.offset; fp.tilesX = share.tilesX; fp.pitchX = share.pitchX; fp.ownedTiles = share.ownedTiles;
     fp.tileAngle = 8.0f * 2.0f * P.tanHalfFovX / (float)c->W;
+    fp.sharedBatches = c->opt.sharedBatches; fp.vplBatches = c->opt.vplBatches; fp.skipMax = c->opt.clusterSkipMax;
     if (fp.ownedTiles == 0) return cudaSuccess;
     c->stats.gatherPairs += share.pixels * (uint64_t)count;
     if (count == 0) {

@@ -951,30 +951,31 @@ __global__ void __launch_bounds__(256) splat_tile_kernel(SplatParams sp, TileGri
         for (uint32_t k = threadIdx.x; k < nb * SPLAT_PREP_F4; k += blockDim.x)
             batch[k] = __ldg(prep + (size_t)tileList[first + base + k / SPLAT_PREP_F4] * SPLAT_PREP_F4 + k % SPLAT_PREP_F4);
         __syncthreads();
-        // phase 0: which staged photons can touch this warp's 8x4-texel sub-block at all?  Lane l tests photons l and l + 32
-        // against the box of the sub-block's surface points (sphere vs. box, with a margin far above the rounding of the exact
-        // test below, so the cull never changes a decision); a photon's footprint covers a few of the tile's eight sub-blocks.
-        unsigned long long cand = 0ull;
+        // phase 0 + 1, per half of the batch: lane l asks whether photon l of the half can touch this warp's 8x4-texel
+        // sub-block at all (sphere vs. the box of the sub-block's surface points, with a margin far above the rounding of the
+        // exact test, so the cull never changes a decision; a footprint covers a few of the tile's eight sub-blocks), then
+        // every texel runs the exact radius test against the survivors only (warp-uniform loop) -> 64-bit hit mask
+        unsigned hitsLo = 0u, hitsHi = 0u;
 #pragma unroll
         for (int h = 0; h < SPLAT_BATCH / 32; h++) {
-            const uint32_t j = (uint32_t)(lane + 32 * h);
+            const uint32_t jl = (uint32_t)(lane + 32 * h);
             bool keep = false;
-            if (j < nb) {
-                const float4 p0 = batch[j * SPLAT_PREP_F4];
+            if (jl < nb) {
+                const float4 p0 = batch[jl * SPLAT_PREP_F4];
                 const float dx = fmaxf(fmaxf(blo.x - p0.x, p0.x - bhi.x), 0.0f), dy = fmaxf(fmaxf(blo.y - p0.y, p0.y - bhi.y), 0.0f),
                             dz = fmaxf(fmaxf(blo.z - p0.z, p0.z - bhi.z), 0.0f);
                 keep = !(dx * dx + dy * dy + dz * dz > r2Cull);
             }
-            cand |= (unsigned long long)__ballot_sync(0xffffffffu, keep) << (32 * h);
+            unsigned hm = 0u;
+            for (unsigned cm = __ballot_sync(0xffffffffu, keep); cm; cm &= cm - 1u) {
+                const int b = __ffs((int)cm) - 1;
+                const float4 p0 = batch[(b + 32 * h) * SPLAT_PREP_F4];
+                const V3 d = v3(p0.x, p0.y, p0.z) - sf.pos;
+                if (!(dot(d, d) > r2)) hm |= 1u << b;
+            }
+            if (h == 0) hitsLo = hm; else hitsHi = hm;
         }
-        // phase 1: exact radius test of this texel against the surviving photons -> 64-bit hit mask (warp-uniform loop)
-        unsigned long long hits = 0ull;
-        for (unsigned long long cm = cand; cm; cm &= cm - 1ull) {
-            const int j = __ffsll((long long)cm) - 1;
-            const float4 p0 = batch[j * SPLAT_PREP_F4];
-            const V3 d = v3(p0.x, p0.y, p0.z) - sf.pos;
-            if (valid && !(dot(d, d) > r2)) hits |= 1ull << j;
-        }
+        unsigned long long hits = valid ? (((unsigned long long)hitsHi << 32) | hitsLo) : 0ull;
         // phase 2: every lane shades ITS OWN hits (ascending j), so a warp iterates max-hits-per-lane times instead of
         // once per photon that any of its lanes touches
         while (hits) {
@@ -1417,15 +1418,14 @@ __global__ void count_flags_kernel(const EvplpRecord* __restrict__ records, uint
 }
 
 cudaError_t launch_count_flags(EvplpContext* c, unsigned long long counts[2]) {
-    unsigned long long* d = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, 16);
+    cudaError_t e = c->scratch64.reserve(2);   // owned by the handle: no allocation per call
     if (e != cudaSuccess) return e;
+    unsigned long long* d = c->scratch64.p;
     cudaMemsetAsync(d, 0, 16, c->stream);
     count_flags_kernel<<<148 * 8, 256, 0, c->stream>>>(c->records.p, c->numRecords, d);
     c->launches++;
     e = cudaMemcpyAsync(counts, d, 16, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d);
     return e;
 }
 
