@@ -378,13 +378,14 @@ def run_gpu(args):
             times.append(time.perf_counter() - t0)
         ms4 = C.c_float()
         ck(lib.evplp_last_stage_ms(h4, capi.STAGE_GATHER, C.byref(ms4)), "stage_ms")
-        fr = torch.tensor([float(np.mean(times)), ms4.value, -ms4.value], dtype=torch.float64, device=f"cuda:{local_rank}")
+        fr = torch.tensor([float(np.median(times)), ms4.value, -ms4.value], dtype=torch.float64, device=f"cuda:{local_rank}")
         if world > 1:
             dist.all_reduce(fr, op=dist.ReduceOp.MAX)
         single = {"workload": "buddha-like statue scene 1.06 M triangles, 3840x2160, numVplLightPaths=1024, numLightPaths=300000: ONE "
                               "iteration split over the GPUs by 8x4-pixel tiles (gather) and light-path ranges (splat), one all-reduce",
                   "frame_ms": float(fr[0]) * 1e3, "gather_ms_slowest_rank": float(fr[1]), "gather_ms_fastest_rank": -float(fr[2]),
-                  "n_gpus": world, "timing": "wall clock around iterate + all-reduce + barrier, mean of 3 frames, max over ranks"}
+                  "n_gpus": world, "timing": "wall clock around iterate + all-reduce + barrier, median of 3 frames, max over ranks",
+                  "frame_ms_all": [round(t * 1e3, 2) for t in times]}
         t4.close()
 
     if rank == 0:
