@@ -118,6 +118,7 @@ SYMBOLS = {
     "evplp_download_accum": (C.c_int, [_P, _P, _P, _P]),
     "evplp_debug_uniforms": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
     "evplp_debug_curand": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
+    "evplp_debug_xorwow_tables": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "evplp_debug_math": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint32, _P]),
     "evplp_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "evplp_reset_stats": (C.c_int, [_P]),
