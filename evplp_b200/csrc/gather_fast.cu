@@ -28,7 +28,7 @@ constexpr int FG_CAND = 96;        // candidate leaves per batch of a descent (a
 constexpr int FG_SPLIT_ROUNDS = 3;  // depth groups per tile: up to 2^rounds
 constexpr float FG_SPLIT_RATIO = 2.5f;   // a group is cut while its distance range exceeds this many tile widths
 constexpr int FG_STACK = 96;       // inner-node stack of the descent (also the packet fallback's stack)
-constexpr int FG_SHAFT_WORDS = 16;  // the cluster shaft's constants (warp-uniform: kept in shared memory, not in registers)
+constexpr int FG_SHAFT_WORDS = 24;  // the cluster shaft's constants (words 0-12) and the depth group's tile box (16-21): warp-uniform, kept in shared memory, not in registers
 constexpr int FG_WARP_WORDS = FG_CL_MAX * FG_PV * 4 + FG_STACK + 7 * FG_CAND + FG_SHAFT_WORDS;
 
 struct FastParams {
@@ -234,13 +234,24 @@ __device__ __forceinline__ int shaft_collect_batch(const DevScene& sc, uint32_t 
 // Exact visibility of one VPL's rays against the warp's current candidate batch.  FILTER: the batch came from a CLUSTER shaft,
 // so it is first filtered, 32 candidates at a time (one per lane), against the thin shaft (VPL -> tile); without FILTER the
 // batch came from that thin shaft itself.  Survivors: per-ray slab test of the leaf box, then the exact triangle tests.
+// the depth group's box of surface points (the far end of every shaft), parked in the warp's shared-memory slice
+__device__ __forceinline__ V3 ld_tile_lo(uint32_t shaftBase) { return v3(ld_shared_f32(shaftBase + 64u), ld_shared_f32(shaftBase + 68u), ld_shared_f32(shaftBase + 72u)); }
+__device__ __forceinline__ V3 ld_tile_hi(uint32_t shaftBase) { return v3(ld_shared_f32(shaftBase + 76u), ld_shared_f32(shaftBase + 80u), ld_shared_f32(shaftBase + 84u)); }
+// G-buffer texel re-read where it is needed (L1-resident) instead of living in registers across the visibility phase; volatile so
+// that the compiler does not hoist the load back out of the cluster loop
+__device__ __forceinline__ float4 ld_texel(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 template <bool FILTER>
-__device__ __forceinline__ bool test_batch(const DevScene& sc, uint32_t candBase, int cn, bool active, V3 org, V3 dir, V3 tlo, V3 thi,
+__device__ __forceinline__ bool test_batch(const DevScene& sc, uint32_t candBase, int cn, bool active, V3 org, V3 dir, uint32_t shaftBase,
                                            float tmin, float tmax) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     DShaft ts;
-    if (FILTER) ts = make_dshaft(org, org, tlo, thi);
+    if (FILTER) ts = make_dshaft(org, org, ld_tile_lo(shaftBase), ld_tile_hi(shaftBase));
     RaySlabM rs;
     bool haveSlab = false, occ = false;
     for (int c0 = 0; c0 < cn; c0 += 32) {
@@ -358,9 +369,9 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
         const bool inside = tx < fp.tilesX && x < gp.x1 && y < gp.y1;
         const size_t n = (size_t)gp.W * gp.H;
         const size_t i = inside ? (size_t)y * gp.W + x : 0;
-        const float4 g0 = gbuf[i], g1 = gbuf[n + i];
+        const float4 g0 = gbuf[i];
         const bool valid = inside && g0.w != 0.0f;
-        const float px = g0.x, py = g0.y, pz = g0.z, nx = g1.x, ny = g1.y, nz = g1.z;
+        const float px = g0.x, py = g0.y, pz = g0.z;
         // A tile whose surface points spread over a long range of distances -- a depth edge inside it, or a floor seen at a
         // grazing angle -- has a long box, and every shaft towards it is a wide fan that meets far more geometry than its 32 rays
         // do.  Its lanes are split by distance from the camera, in up to three rounds of "cut the group's range in the middle
@@ -393,10 +404,16 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
         for (unsigned gmask = groupsPresent; gmask; gmask &= gmask - 1u) {
         const bool vg = valid && grp == (__ffs((int)gmask) - 1);
         // bounds of the group's surface points: the far end of every shaft
-        V3 tlo = vg ? v3(px, py, pz) : v3s(INFINITY), thi = vg ? v3(px, py, pz) : v3s(-INFINITY);
-        for (int o = 16; o > 0; o >>= 1) {
-            tlo = v3(fminf(tlo.x, __shfl_xor_sync(full, tlo.x, o)), fminf(tlo.y, __shfl_xor_sync(full, tlo.y, o)), fminf(tlo.z, __shfl_xor_sync(full, tlo.z, o)));
-            thi = v3(fmaxf(thi.x, __shfl_xor_sync(full, thi.x, o)), fmaxf(thi.y, __shfl_xor_sync(full, thi.y, o)), fmaxf(thi.z, __shfl_xor_sync(full, thi.z, o)));
+        {
+            V3 tlo = vg ? v3(px, py, pz) : v3s(INFINITY), thi = vg ? v3(px, py, pz) : v3s(-INFINITY);
+            for (int o = 16; o > 0; o >>= 1) {
+                tlo = v3(fminf(tlo.x, __shfl_xor_sync(full, tlo.x, o)), fminf(tlo.y, __shfl_xor_sync(full, tlo.y, o)), fminf(tlo.z, __shfl_xor_sync(full, tlo.z, o)));
+                thi = v3(fmaxf(thi.x, __shfl_xor_sync(full, thi.x, o)), fmaxf(thi.y, __shfl_xor_sync(full, thi.y, o)), fmaxf(thi.z, __shfl_xor_sync(full, thi.z, o)));
+            }
+            __syncwarp();   // (every lane writes the same words)
+            st_shared_u32(shaftBase + 64u, __float_as_uint(tlo.x)); st_shared_u32(shaftBase + 68u, __float_as_uint(tlo.y)); st_shared_u32(shaftBase + 72u, __float_as_uint(tlo.z));
+            st_shared_u32(shaftBase + 76u, __float_as_uint(thi.x)); st_shared_u32(shaftBase + 80u, __float_as_uint(thi.y)); st_shared_u32(shaftBase + 84u, __float_as_uint(thi.z));
+            __syncwarp();
         }
         int skipLeft = 0, skipLen = 0;   // clusters that go straight to per-VPL descents after a fat cluster shaft
         for (uint32_t c = cBegin; c < cEnd; c++) {
@@ -406,13 +423,20 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
             for (int k = lane; k < nb * FG_PV; k += 32) spv[k] = __ldg(pv + (size_t)first * FG_PV + k);
             __syncwarp();
             // which VPLs of the cluster light any pixel of the tile at all (cosine test of vplSplat, lighttracing.cu:282-288)
-            unsigned live = 0u;
-            for (int j = 0; j < nb; j++) {
-                const float4 a = spv[j * FG_PV], b = spv[j * FG_PV + 1];
-                const float vx = a.x - px, vy = a.y - py, vz = a.z - pz;
-                const float c1 = fmaxf(nx * vx + ny * vy + nz * vz, 0.0f);
-                const float c2 = fmaxf(-(b.x * vx + b.y * vy + b.z * vz), 0.0f);
-                if (__any_sync(full, vg && !(c1 * c2 <= 0.000f))) live |= 1u << j;
+            // (actBits: bit j = THIS lane's pixel passes it; the visibility loops below only read bits, so the pixel's normal is not
+            // live across them)
+            unsigned live = 0u, actBits = 0u;
+            {
+                const float4 g1 = ld_texel(gbuf + n + i);
+                for (int j = 0; j < nb; j++) {
+                    const float4 a = spv[j * FG_PV], b = spv[j * FG_PV + 1];
+                    const float vx = a.x - px, vy = a.y - py, vz = a.z - pz;
+                    const float c1 = fmaxf(g1.x * vx + g1.y * vy + g1.z * vz, 0.0f);
+                    const float c2 = fmaxf(-(b.x * vx + b.y * vy + b.z * vz), 0.0f);
+                    const bool act = vg && !(c1 * c2 <= 0.000f);
+                    if (act) actBits |= 1u << j;
+                    if (__any_sync(full, act)) live |= 1u << j;
+                }
             }
             FG_HIST(hist[8]++;)              // (cluster, tile) pairs with a valid pixel
             FG_PROF_END(1);
@@ -431,7 +455,7 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
                 const float4 bl = __ldg(cbox + 2 * (size_t)c), bh = __ldg(cbox + 2 * (size_t)c + 1);
                 descents++;
                 __syncwarp();
-                store_shaft(shaftBase, make_dshaft(v3(bl.x, bl.y, bl.z), v3(bh.x, bh.y, bh.z), tlo, thi));
+                store_shaft(shaftBase, make_dshaft(v3(bl.x, bl.y, bl.z), v3(bh.x, bh.y, bh.z), ld_tile_lo(shaftBase), ld_tile_hi(shaftBase)));
                 st_shared_u32(stackBase, 0u);   // root (every lane writes the same word)
                 uint32_t sp = stackBase + 4u;
                 __syncwarp();
@@ -446,13 +470,11 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
                         batches++;
                         for (unsigned m = live; m; m &= m - 1u) {
                             const int j = __ffs((int)m) - 1;
-                            const float4 a = spv[j * FG_PV], b = spv[j * FG_PV + 1];
-                            const float vx = a.x - px, vy = a.y - py, vz = a.z - pz;   // v12 = vpl.pos - x
-                            const float c1 = fmaxf(nx * vx + ny * vy + nz * vz, 0.0f);
-                            const float c2 = fmaxf(-(b.x * vx + b.y * vy + b.z * vz), 0.0f);
-                            const bool active = vg && !(c1 * c2 <= 0.000f) && !((occBits >> j) & 1u);
+                            const bool active = ((actBits & ~occBits) >> j) & 1u;
                             if (!__any_sync(full, active)) continue;
-                            if (test_batch<true>(sc, candBase, cn, active, v3(a.x, a.y, a.z), v3(-vx, -vy, -vz), tlo, thi, tmin, tmax)) occBits |= 1u << j;
+                            const float4 a = spv[j * FG_PV];
+                            const float vx = a.x - px, vy = a.y - py, vz = a.z - pz;   // v12 = vpl.pos - x
+                            if (test_batch<true>(sc, candBase, cn, active, v3(a.x, a.y, a.z), v3(-vx, -vy, -vz), shaftBase, tmin, tmax)) occBits |= 1u << j;
                         }
                         FG_PROF_END(3);
                     }
@@ -471,16 +493,14 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
             if (!shared) {
                 for (unsigned m = live; m; m &= m - 1u) {
                     const int j = __ffs((int)m) - 1;
-                    const float4 a = spv[j * FG_PV], b = spv[j * FG_PV + 1];
-                    const float vx = a.x - px, vy = a.y - py, vz = a.z - pz;   // v12 = vpl.pos - x
-                    const float c1 = fmaxf(nx * vx + ny * vy + nz * vz, 0.0f);
-                    const float c2 = fmaxf(-(b.x * vx + b.y * vy + b.z * vz), 0.0f);
-                    const bool active = vg && !(c1 * c2 <= 0.000f) && !((occBits >> j) & 1u);
+                    const bool active = ((actBits & ~occBits) >> j) & 1u;
                     if (!__any_sync(full, active)) continue;
+                    const float4 a = spv[j * FG_PV];
+                    const float vx = a.x - px, vy = a.y - py, vz = a.z - pz;   // v12 = vpl.pos - x
                     const V3 org = v3(a.x, a.y, a.z), dir = v3(-vx, -vy, -vz);
                     descents++;
                     __syncwarp();
-                    store_shaft(shaftBase, make_dshaft(org, org, tlo, thi));
+                    store_shaft(shaftBase, make_dshaft(org, org, ld_tile_lo(shaftBase), ld_tile_hi(shaftBase)));
                     st_shared_u32(stackBase, 0u);
                     uint32_t sp = stackBase + 4u;
                     __syncwarp();
@@ -493,7 +513,7 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
                         if (cn > 0) {
                             candTotal += (unsigned)cn;
                             batches++;
-                            occ |= test_batch<false>(sc, candBase, cn, active && !occ, org, dir, tlo, thi, tmin, tmax);
+                            occ |= test_batch<false>(sc, candBase, cn, active && !occ, org, dir, shaftBase, tmin, tmax);
                             FG_PROF_END(5);
                             if (!__any_sync(full, active && !occ)) break;                  // every ray has its answer
                         }
@@ -514,7 +534,8 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
             // ---- shading of the unoccluded pairs.  The pixel's BRDF terms are re-derived per cluster (two L1-resident loads and
             // ~25 instructions per 16 VPLs) instead of occupying 11 registers during the visibility phase:
             // r1 = reflect(-wi10, n), so that dot(wi10, reflect(-wi12, n)) = dot(r1, wi12)
-            const float4 g2 = gbuf[2 * n + i], g3 = gbuf[3 * n + i];
+            const float4 g1 = ld_texel(gbuf + n + i), g2 = ld_texel(gbuf + 2 * n + i), g3 = ld_texel(gbuf + 3 * n + i);
+            const float nx = g1.x, ny = g1.y, nz = g1.z;
             float r1x, r1y, r1z;
             {
                 const float wx = gp.cameraPosition.x - px, wy = gp.cameraPosition.y - py, wz = gp.cameraPosition.z - pz;
@@ -534,7 +555,7 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
                 const float c1 = fmaxf(nx * vx + ny * vy + nz * vz, 0.0f);
                 const float c2 = fmaxf(-(b.x * vx + b.y * vy + b.z * vz), 0.0f);
                 const float c1c2 = c1 * c2;
-                const bool active = vg && !(c1c2 <= 0.000f);
+                const bool active = (actBits >> j) & 1u;
                 rays += active ? 1u : 0u;
                 steps++;
                 if (active && !((occBits >> j) & 1u)) {
