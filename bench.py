@@ -162,6 +162,13 @@ def _oracle_gbuffer_tile(orc, P, tile):
     return planes[:, y0:y1, x0:x1, :], prims[y0:y1, x0:x1]
 
 
+def config_dict(world):
+    """The `config` object of the JSON line: identical in both arms (the reference arm times the same workload on the host)."""
+    return {"workload": WORKLOAD, "partition": f"iterations round-robin over {world} GPU(s), one all-reduce of the "
+            "int64 accumulation layers per timed batch", "l2": "inputs larger than L2: per iteration 133 MB G-buffer + "
+            "115 MB records + 100 MB accumulators are rewritten/re-read"}
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -171,8 +178,10 @@ def run_reference(args):
         "impl": "reference", "metric": "VPL-pixel pairs/s", "value": pps, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "the reference (VS2015 + CUDA 8 + OptiX 4.1.1 + OpenGL) cannot be built or run "
-                   "here; this arm times the scalar C++ restatement of its device programs (oracle/) on the host cores"},
+        "config": config_dict(args.gpus),
+        "note": "the reference (VS2015 + CUDA 8 + OptiX 4.1.1 + OpenGL) cannot be built or run here; this arm times the scalar C++ "
+                "restatement of its device programs (oracle/, pinned against the reference's own device code: DESIGN.md section 2) on "
+                "the host cores, on a bounded sample of the same workload",
         "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -408,15 +417,16 @@ def run_gpu(args):
             traffic_src = ("; traffic = dram__bytes_read + dram__bytes_write of one launch of this workload "
                            "(profiles/r2_gather_traffic_headline.json: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of that "
                            "launch): G-buffer planes, prepared VPLs, accumulators and whatever BVH data misses the L2")
+        straffic, spath = None, os.path.join(ROOT, "profiles", "r2_splat_traffic_headline.json")
+        if not overridden and os.path.exists(spath):   # dram bytes of splat_prepare + splat_fill + splat_tile of one iteration of this workload
+            straffic = json.load(open(spath))["traffic_bytes_per_launch"]
         nrec = PHOTONFAM["numLightPaths"] * 4
         splat_bytes = (96.0 * nrec + 64.0 * RES_X * RES_Y + 48.0 * RES_X * RES_Y) * args.steps
         line = {
             "metric": "VPL-pixel pairs/s", "value": pairs / sec, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "partition": f"iterations round-robin over {world} GPU(s), one all-reduce of the "
-                       "int64 accumulation layers per timed batch", "l2": "inputs larger than L2: per iteration 133 MB G-buffer + "
-                       "115 MB records + 100 MB accumulators are rewritten/re-read"},
+            "config": config_dict(world),
             # photons / fragments per second of the WHOLE step (the gather takes 99.9 % of it) and of the splat stage alone
             "splatted_photons_per_s": photons / sec, "splat_fragments_per_s": frags / sec, "shadow_rays_per_s": rays / sec,
             "splat_stage_photons_per_s": my_photons / splat_s * world, "light_trace_stage_paths_per_s":
@@ -434,8 +444,10 @@ def run_gpu(args):
                                  "triangle tests ~40 % of the issued instructions, hierarchy descents + shaft tests ~35 %, shading ~11 %; "
                                  "DRAM < 0.1 % of peak)" + traffic_src},
             "roofline_splat": {"kernel": "splat_prepare + splat_fill + splat_tile_kernel", "bound": "hbm", "achieved": splat_bytes / splat_s / 1e9, "peak": hbm,
-                               "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": None,
-                               "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}"},
+                               "unit": "GB/s", "frac": splat_bytes / splat_s / 1e9 / hbm, "traffic": straffic,
+                               "note": f"96 B x records + 64 B x px + 48 B x px per launch; peak {how}; traffic = dram bytes of the three kernels of "
+                                       "one iteration (profiles/r2_splat_traffic_headline.json); at the reference's radius the splat is bound by "
+                                       "fragment shading, not bytes (DESIGN.md section 4)"},
             "clocks": clk, "gpu_launches": int(l1 - l0),
             "same_job_checksums": check, "single_frame_strong_scaling": single,
             "e2e": {"value": e2e_pairs / e2e_sec, "unit": "pairs/s", "h2d_bytes_per_step": 3200 + C.sizeof(capi.Params),
