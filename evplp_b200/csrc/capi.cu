@@ -119,7 +119,7 @@ int evplp_destroy(evplp_handle c) {
     c->refitFlags.release(); c->nodes.release(); c->shaftNodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
     c->gatherCost.release(); c->gatherCostSorted.release(); c->gatherIota.release(); c->gatherOrder.release();
     c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->skipTable.release(); c->scratch64.release(); c->records.release();
-    c->vplList.release(); c->vplKeys.release(); c->vplKeysSorted.release(); c->vplVals.release(); c->vplOrder.release(); c->vplPrepared.release(); c->clusterBox.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
+    c->vplList.release(); c->vplKeys.release(); c->vplKeysSorted.release(); c->vplVals.release(); c->vplOrder.release(); c->vplPrepared.release(); c->clusterBox.release(); c->clusterSlots.release(); c->clusterList.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
     c->accPhoton.release(); c->accLight.release(); c->accCount.release(); c->resolveOut.release(); c->devStats.release();
     if (c->resolvePinned) cudaFreeHost(c->resolvePinned);
     for (int s = 0; s < ST_COUNT; s++) { cudaEventDestroy(c->stageA[s]); cudaEventDestroy(c->stageB[s]); }
@@ -672,7 +672,7 @@ int evplp_set_option(evplp_handle c, const char* name, int value) {
         {"shaft_max_candidates", &o.shaftCandMax, 1, evplp::SHAFT_CAND}, {"shaft_streak", &o.shaftStreak, 1, 1 << 20},
         {"shaft_skip", &o.shaftSkip, 0, 1 << 20},
         {"gather_shared_batches", &o.sharedBatches, 1, 1 << 20}, {"gather_vpl_batches", &o.vplBatches, 1, 1 << 20},
-        {"gather_cluster_skip_max", &o.clusterSkipMax, 0, 1 << 20},
+        {"gather_cluster_skip_max", &o.clusterSkipMax, 0, 1 << 20}, {"gather_cluster_extent_permille", &o.clusterExtentPermille, 0, 1000},
         {"gather_lpt", &o.gatherLpt, 0, 1}, {"gather_persistent", &o.gatherPersistent, 0, 1},
         {"splat_group", &o.splatGroup, 0, 32}, {"splat_mode", &o.splatMode, 0, 1}, {"splat_max_entries", &splatMaxEntries, 0, 0x7fffffff},
         {"bvh_leaf_max", &o.bvhLeafMax, 1, 8}, {"shaft_leaf_max", &o.shaftLeafMax, 1, 8},

@@ -45,6 +45,7 @@ struct Options {
     int gatherMode = 1;          // 1 = shaft traversal of the 32-wide hierarchy, 0 = per-ray packet traversal, 2 = shaft in VSL too
     int gatherAlgo = 1;          // 1 = VPL-cluster gather (tolerance mode, default), 0 = per-VPL exact-order gather
     int clusterSize = 16;        // VPLs per cluster of the cluster gather
+    int clusterExtentPermille = 70;  // cluster gather: a run of clusterSize VPLs whose box edge exceeds this many 1/1000 of the scene's longest edge is cut into halves / quarters (0 = never)
     int sharedBatches = 3, vplBatches = 3, clusterSkipMax = 64;   // cluster gather: candidate batches a shared / a per-VPL descent may stream; longest run of clusters that skip the shared attempt after a fat shaft
     int shaftCandMax = 128, shaftStreak = 3, shaftSkip = 256;
     int gatherLpt = 1, gatherPersistent = 1;
@@ -112,6 +113,7 @@ struct EvplpContext {
     // and the cluster boxes (2 float4 each)
     evplp::DevBuf<uint32_t> vplKeys, vplKeysSorted, vplVals, vplOrder;
     evplp::DevBuf<float4> vplPrepared, clusterBox;
+    evplp::DevBuf<uint32_t> clusterSlots, clusterList;   // cluster layout of the cluster gather: packed (first << 5 | count)
     evplp::DevBuf<uint32_t> photonList;           // indices of usable photon records
     evplp::DevBuf<float4> splatPrep;              // per-photon constants of the fragment shader (5 float4 each)
     evplp::DevBuf<uint32_t> tileCount, tileOffset, tileCursor, tileList;  // photon bins of the tiled splat

@@ -16,6 +16,7 @@
 // polynomial pow (relative error < 1e-5 per pair, measured; north_star tolerance for radiance: 1e-4 per pixel).  The
 // bit-exact path stays available (gather_chunks = 1 or gather_algo = 0) and is what the parity tests compare bit for bit.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include "context.h"
 
 namespace evplp {
@@ -34,7 +35,9 @@ constexpr int FG_WARP_WORDS = FG_CL_MAX * FG_PV * 4 + FG_STACK + 7 * FG_CAND + F
 struct FastParams {
     GatherParams g;
     int clusterSize;
-    uint32_t numClusters, count;
+    uint32_t count;
+    const uint32_t* clusterList;    // packed (first << 5 | count) per cluster, Morton order
+    const uint32_t* numClusters;    // how many (device: the layout is cut on the device)
     int tilesX, pitchX;             // 8x4-pixel tiles per row of the launch rectangle; row pitch of the tile numbering
     uint32_t ownedTiles;            // tiles t = offset + k * stride, k < ownedTiles (this handle's share of the image)
     uint32_t stride, offset;
@@ -112,11 +115,52 @@ __global__ void vpl_prepare_kernel(const EvplpRecord* __restrict__ records, cons
     o[5] = make_float4(f.x, f.y, f.z, 0.0f);
 }
 
-__global__ void cluster_bounds_kernel(const float4* __restrict__ pv, uint32_t count, int clusterSize, uint32_t numClusters,
-                                      float4* __restrict__ cbox) {
+// Cluster layout.  The Morton order jumps across the scene wherever a high bit of the code changes, and a run of `clusterSize`
+// VPLs that spans such a jump has a box far larger than its VPLs need -- a fat double shaft for every tile.  Each run is therefore
+// kept whole only while its box is small (longest edge <= maxExtent); otherwise it is cut into halves, and those once more into
+// quarters (never below 4 VPLs).  Output: up to 4 packed words (first << 5 | count, count = 0: unused) per run.
+__global__ void cluster_layout_kernel(const float4* __restrict__ pv, uint32_t count, int clusterSize, uint32_t numRuns, float maxExtent,
+                                      uint32_t* __restrict__ slots) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numRuns) return;
+    const uint32_t first = r * (uint32_t)clusterSize, n = min((uint32_t)clusterSize, count - first);
+    auto extent = [&](uint32_t a, uint32_t b) {   // longest edge of the box of VPLs [a, b)
+        float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+        for (uint32_t j = a; j < b; j++) {
+            const float4 p = pv[(size_t)j * FG_PV];
+            lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
+            hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
+        }
+        return fmaxf(hx - lx, fmaxf(hy - ly, hz - lz));
+    };
+    uint32_t out[4] = {0u, 0u, 0u, 0u};
+    int k = 0;
+    if (n < 8u || !(extent(first, first + n) > maxExtent)) {
+        out[k++] = (first << 5) | n;
+    } else {
+        const uint32_t h = n / 2;
+        for (int half = 0; half < 2; half++) {
+            const uint32_t a = first + (half ? h : 0u), m = half ? n - h : h;
+            if (m < 8u || !(extent(a, a + m) > maxExtent)) {
+                out[k++] = (a << 5) | m;
+            } else {
+                out[k++] = (a << 5) | (m / 2);
+                out[k++] = ((a + m / 2) << 5) | (m - m / 2);
+            }
+        }
+    }
+    for (int q = 0; q < 4; q++) slots[4 * (size_t)r + q] = out[q];
+}
+
+struct ClusterUsed {
+    __device__ bool operator()(uint32_t w) const { return (w & 31u) != 0u; }
+};
+
+__global__ void cluster_bounds_kernel(const float4* __restrict__ pv, const uint32_t* __restrict__ clusterList,
+                                      const uint32_t* __restrict__ numClusters, float4* __restrict__ cbox) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= numClusters) return;
-    const uint32_t first = c * (uint32_t)clusterSize, last = min(count, first + (uint32_t)clusterSize);
+    if (c >= *numClusters) return;
+    const uint32_t w = clusterList[c], first = w >> 5, last = first + (w & 31u);
     float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
     for (uint32_t j = first; j < last; j++) {
         const float4 p = pv[(size_t)j * FG_PV];
@@ -397,9 +441,10 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
         FG_PROF_END(8);
         unsigned groupsPresent = 0u;
         for (int g = 0; g < (1 << FG_SPLIT_ROUNDS); g++) if (__any_sync(full, valid && grp == g)) groupsPresent |= 1u << g;
-        const uint32_t per = (fp.numClusters + fp.numChunks - 1) / fp.numChunks;
-        const uint32_t cBegin = min(fp.numClusters, chunk * per);
-        const uint32_t cEnd = min(fp.numClusters, cBegin + per);
+        const uint32_t numClusters = __ldg(fp.numClusters);
+        const uint32_t per = (numClusters + fp.numChunks - 1) / fp.numChunks;
+        const uint32_t cBegin = min(numClusters, chunk * per);
+        const uint32_t cEnd = min(numClusters, cBegin + per);
         float resx = 0.f, resy = 0.f, resz = 0.f;
         for (unsigned gmask = groupsPresent; gmask; gmask &= gmask - 1u) {
         const bool vg = valid && grp == (__ffs((int)gmask) - 1);
@@ -417,8 +462,9 @@ gather_cluster_kernel(DevScene sc, FastParams fp, const float4* __restrict__ gbu
         }
         int skipLeft = 0, skipLen = 0;   // clusters that go straight to per-VPL descents after a fat cluster shaft
         for (uint32_t c = cBegin; c < cEnd; c++) {
-            const uint32_t first = c * (uint32_t)fp.clusterSize;
-            const int nb = (int)min((uint32_t)fp.clusterSize, fp.count - first);
+            const uint32_t cw = __ldg(fp.clusterList + c);
+            const uint32_t first = cw >> 5;
+            const int nb = (int)(cw & 31u);
             __syncwarp();
             for (int k = lane; k < nb * FG_PV; k += 32) spv[k] = __ldg(pv + (size_t)first * FG_PV + k);
             __syncwarp();
@@ -681,7 +727,7 @@ cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile t, GatherParams g, 
     fp.g = g;
     fp.count = count;
     fp.clusterSize = c->opt.clusterSize < 1 ? 1 : (c->opt.clusterSize > FG_CL_MAX ? FG_CL_MAX : c->opt.clusterSize);
-    fp.numClusters = (count + (uint32_t)fp.clusterSize - 1) / (uint32_t)fp.clusterSize;
+    const uint32_t numRuns = (count + (uint32_t)fp.clusterSize - 1) / (uint32_t)fp.clusterSize;   // nominal clusters (before cuts)
     const TileShare share = tile_share(c, t);
     fp.stride = share.stride; fp.offset = share.offset; fp.tilesX = share.tilesX; fp.pitchX = share.pitchX; fp.ownedTiles = share.ownedTiles;
     fp.tileAngle = 8.0f * 2.0f * P.tanHalfFovX / (float)c->W;
@@ -701,7 +747,8 @@ cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile t, GatherParams g, 
     FG_CK(c->vplKeys.reserve(count)); FG_CK(c->vplKeysSorted.reserve(count)); FG_CK(c->vplOrder.reserve(count));
     FG_CK(c->vplVals.reserve(count));
     FG_CK(c->vplPrepared.reserve((size_t)count * FG_PV));
-    FG_CK(c->clusterBox.reserve((size_t)fp.numClusters * 2));
+    FG_CK(c->clusterBox.reserve((size_t)numRuns * 4 * 2));
+    FG_CK(c->clusterSlots.reserve((size_t)numRuns * 4)); FG_CK(c->clusterList.reserve((size_t)numRuns * 4 + 1));
     float3 smin = make_float3(c->sceneMin[0], c->sceneMin[1], c->sceneMin[2]), scale;
     scale.x = 1024.0f / fmaxf(c->sceneMax[0] - c->sceneMin[0], 1e-20f);
     scale.y = 1024.0f / fmaxf(c->sceneMax[1] - c->sceneMin[1], 1e-20f);
@@ -713,8 +760,18 @@ cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile t, GatherParams g, 
     FG_CK(c->sortTemp.reserve(tempBytes));
     FG_CK(cub::DeviceRadixSort::SortPairs(c->sortTemp.p, tempBytes, c->vplKeys.p, c->vplKeysSorted.p, c->vplVals.p, c->vplOrder.p, (int)count, 0, 30, st));
     vpl_prepare_kernel<<<pb, 256, 0, st>>>(c->records.p, c->vplOrder.p, count, c->vplPrepared.p);
-    cluster_bounds_kernel<<<(fp.numClusters + 127) / 128, 128, 0, st>>>(c->vplPrepared.p, count, fp.clusterSize, fp.numClusters, c->clusterBox.p);
-    c->launches += 5;
+    // cluster layout: runs of clusterSize, cut where the Morton order jumps (box edge > extent permille of the scene's longest edge)
+    const float sceneEdge = fmaxf(c->sceneMax[0] - c->sceneMin[0], fmaxf(c->sceneMax[1] - c->sceneMin[1], c->sceneMax[2] - c->sceneMin[2]));
+    const float maxExtent = c->opt.clusterExtentPermille > 0 ? sceneEdge * (float)c->opt.clusterExtentPermille * 0.001f : INFINITY;
+    uint32_t* devNumClusters = c->clusterList.p + (size_t)numRuns * 4;
+    cluster_layout_kernel<<<(numRuns + 127) / 128, 128, 0, st>>>(c->vplPrepared.p, count, fp.clusterSize, numRuns, maxExtent, c->clusterSlots.p);
+    tempBytes = 0;
+    FG_CK(cub::DeviceSelect::If(nullptr, tempBytes, c->clusterSlots.p, c->clusterList.p, devNumClusters, (int)(numRuns * 4), ClusterUsed(), st));
+    FG_CK(c->sortTemp.reserve(tempBytes));
+    FG_CK(cub::DeviceSelect::If(c->sortTemp.p, tempBytes, c->clusterSlots.p, c->clusterList.p, devNumClusters, (int)(numRuns * 4), ClusterUsed(), st));
+    cluster_bounds_kernel<<<(numRuns * 4 + 127) / 128, 128, 0, st>>>(c->vplPrepared.p, c->clusterList.p, devNumClusters, c->clusterBox.p);
+    fp.clusterList = c->clusterList.p; fp.numClusters = devNumClusters;
+    c->launches += 8;
     // ---- work items: (owned tile, cluster range); enough of them per resident warp that the tail stays short
     const unsigned residentBlocks = 148u * 4u;
     const uint64_t residentWarps = (uint64_t)residentBlocks * GATHER_WARPS;
@@ -724,10 +781,10 @@ cudaError_t launch_gather_cluster(EvplpContext* c, EvplpTile t, GatherParams g, 
     } else {
         const uint64_t want = residentWarps * 24u;
         if (fp.ownedTiles < want) chunks = (unsigned)((want + fp.ownedTiles - 1) / fp.ownedTiles);
-        const unsigned maxChunks = (fp.numClusters + 7) / 8;   // at least 8 clusters per range
+        const unsigned maxChunks = (numRuns + 7) / 8;   // at least 8 (nominal) clusters per range
         if (chunks > maxChunks) chunks = maxChunks ? maxChunks : 1;
     }
-    if (chunks > fp.numClusters) chunks = fp.numClusters;
+    if (chunks > numRuns) chunks = numRuns;
     fp.numChunks = chunks;
     fp.g.numChunks = chunks;
     if (chunks > 1 && !P.doAccumulate) {

@@ -90,6 +90,13 @@ def test_cluster_gather_accumulates_tiles_and_small_clusters(rig):
         vpl, _, _ = rig.dev.download_accum()
         assert _errors(vpl, eacc)[0] <= 1e-4, cs
     rig.dev.set_option("gather_cluster_size", 16)
+    # cluster layout: runs of 16 cut into halves / quarters where their box is large (1 = every run is cut, 0 = never, 1000 = whole scene)
+    for permille in (1, 0, 1000, 70):
+        rig.dev.set_option("gather_cluster_extent_permille", permille)
+        rig.dev.clear_accum()
+        rig.dev.vpl_gather(capi.GATHER_VPL)
+        vpl, _, _ = rig.dev.download_accum()
+        assert _errors(vpl, eacc)[0] <= 1e-4, permille
 
 
 def test_two_handles_partition_the_image_between_them(rig):
