@@ -511,7 +511,10 @@ __device__ V3 vsl_shade(const GatherParams& gp, const Surface& sf, V3 wi10, cons
 
 // splatSplotch (lighttracing.cu:689-722): one thread per pixel, the per-pixel XORWOW stream
 // runs through ALL VSLs in order, so the VSL list cannot be split.
-__global__ void __launch_bounds__(GATHER_WARPS * 32)
+#ifndef EVPLP_VSL_MINB
+#define EVPLP_VSL_MINB 2   // blocks / SM the register allocation aims at (tuning: -DEVPLP_VSL_MINB=3 / 4)
+#endif
+__global__ void __launch_bounds__(GATHER_WARPS * 32, EVPLP_VSL_MINB)
 gather_vsl_kernel(DevScene sc, GatherParams gp, const uint32_t* __restrict__ skip, const float4* __restrict__ gbuf,
                   const EvplpRecord* __restrict__ records, const uint32_t* __restrict__ vplList,
                   const uint32_t* __restrict__ vplCount, long long* __restrict__ acc, DevStats* stats) {
