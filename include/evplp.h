@@ -270,8 +270,9 @@ int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
  * order in one thread, which makes the gather bit-identical to the scalar oracle; N > 1 = N contiguous ranges of
  * ceil(total / N) usable VPLs, each summed in record order and added in Q31.32 with integer atomics: deterministic, and
  * bit-identical to the oracle evaluated range by range).
- * "gather_band_stride" / "gather_band_offset": the gather only renders the 16-row bands b = offset (mod stride) of its
- * tile -- the interleaved image partition of a single heavy frame over N GPUs (stride = N, offset = rank).
+ * "gather_band_stride" / "gather_band_offset": the gather only renders the 8x4-pixel tiles t = offset (mod stride) of its
+ * rectangle -- the interleaved image partition of a single heavy frame over N GPUs (stride = N, offset = rank; VSL / LVC gathers:
+ * 16-row bands).
  * "gather_mode": 1 (default) = the warp descends a 32-wide hierarchy with one conservative shaft-vs-box test per child
  * and runs the exact per-ray triangle tests on the collected candidate leaves; 0 = per-ray packet traversal of the 4-wide
  * hierarchy; 2 = shaft traversal in the VSL gather too (sampling-bound: no gain measured).  "shaft_max_candidates" (candidate leaves per step before falling back to mode 0, <= 128 = default),
@@ -285,8 +286,13 @@ int evplp_event_elapsed_ms(evplp_handle h, int slotA, int slotB, float* ms);
  * <= 16, one double-shaft descent per (cluster, 8x4-pixel tile) where the shaft is thin enough, shading tail with FMA
  * contraction: radiance within the 1e-4 tolerance, NOT bit-identical to the oracle) is used 1 (default) = from 16384 usable
  * VPLs on (it needs dense VPLs), 2 = always, 0 = never (the per-VPL exact-order kernel).  gather_chunks = 1 always selects
- * the exact-order kernel (the bit-exact test mode).  Under gather_algo 1 the image partition
- * ("gather_band_stride" / "gather_band_offset") is by 8x4-pixel tiles t = offset (mod stride) instead of 16-row bands.
+ * the exact-order kernel (the bit-exact test mode).  Cluster-gather knobs: "gather_cluster_extent_permille" (default 70: a run
+ * of gather_cluster_size VPLs whose box edge exceeds that many 1/1000 of the scene's longest edge is cut into halves / quarters;
+ * 0 = never), "gather_shared_batches" / "gather_vpl_batches" (default 3 / 3: batches of 96 candidate leaves a cluster's shared
+ * descent / a single VPL's descent may stream before falling back to per-VPL descents / the packet traversal),
+ * "gather_cluster_skip_max" (default 64: longest run of clusters that skip the shared attempt after a fat shaft).
+ * Limits: evplp_photon_splat / evplp_vpl_gather compact at most 2^31 - 1 records per call (stream larger frames in chunks,
+ * as RtComPhoton::runStreamed does).
  * Every handle owns its options: a non-NULL handle sets that handle only; a NULL handle sets the defaults that handles
  * created AFTERWARDS start from.  Values are range-checked (EVPLP_ERR_INVALID). */
 int evplp_set_option(evplp_handle h, const char* name, int value);
