@@ -346,6 +346,53 @@ __global__ void tiny_root_kernel(int n, const float* __restrict__ primLo, const 
 }
 
 
+// Quantised twin of the 4-wide nodes (device_scene.h, CNode).  Every rounding goes outwards: the origin is the exact minimum of the
+// child boxes, offsets are formed with directed subtractions, divided by a power-of-two scale (exact) and floored / ceiled; the
+// scale is the smallest power of two that keeps every high plane within 255 units.
+__global__ void compress_nodes_kernel(const WideNode* __restrict__ nodes, int numNodes, CNode* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numNodes) return;
+    const WideNode nd = nodes[i];
+    const float* lo[3] = {nd.lox, nd.loy, nd.loz};
+    const float* hi[3] = {nd.hix, nd.hiy, nd.hiz};
+    float org[3];
+    uint32_t exps = 0u, ql[3] = {0u, 0u, 0u}, qh[3] = {0u, 0u, 0u};
+    for (int a = 0; a < 3; a++) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int k = 0; k < BVH_WIDTH; k++)
+            if (nd.child[k] != BVH_EMPTY) { mn = fminf(mn, lo[a][k]); mx = fmaxf(mx, hi[a][k]); }
+        if (!(mn <= mx)) { mn = 0.f; mx = 0.f; }   // (a node without children does not occur)
+        org[a] = mn;
+        int e = 0;
+        const float unit = __fdiv_ru(__fsub_ru(mx, mn), 255.0f);
+        if (unit > 0.f) (void)frexpf(unit, &e);     // unit = m 2^e, m in [0.5, 1): 2^e >= unit
+        int biased = e + 127;
+        biased = biased < 1 ? 1 : (biased > 254 ? 254 : biased);
+        for (;;) {
+            const float s = __uint_as_float((uint32_t)biased << 23);
+            bool ok = true;
+            uint32_t wl = 0u, wh = 0u;
+            for (int k = 0; k < BVH_WIDTH; k++) {
+                uint32_t l = 255u, h = 0u;          // empty slot: inverted box (and the traversal checks the child word)
+                if (nd.child[k] != BVH_EMPTY) {
+                    const float fl = floorf(__fdiv_rd(__fsub_rd(lo[a][k], mn), s)), fh = ceilf(__fdiv_ru(__fsub_ru(hi[a][k], mn), s));
+                    if (fh > 255.0f) ok = false;
+                    l = (uint32_t)fmaxf(fl, 0.0f); h = (uint32_t)fminf(fmaxf(fh, 0.0f), 255.0f);
+                }
+                wl |= l << (8 * k); wh |= h << (8 * k);
+            }
+            if (ok || biased >= 254) { ql[a] = wl; qh[a] = wh; break; }
+            biased++;
+        }
+        exps |= (uint32_t)biased << (8 * a);
+    }
+    CNode c;
+    c.ox = org[0]; c.oy = org[1]; c.oz = org[2]; c.exps = exps;
+    for (int k = 0; k < BVH_WIDTH; k++) c.child[k] = nd.child[k];
+    c.qlx = ql[0]; c.qly = ql[1]; c.qlz = ql[2]; c.qhx = qh[0]; c.qhy = qh[1]; c.qhz = qh[2]; c.pad0 = 0u; c.pad1 = 0u;
+    out[i] = c;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { if (err) *err = std::string(#x) + ": " + cudaGetErrorString(e_); return e_; } } while (0)
 
 
@@ -449,6 +496,8 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
     if (n <= c->opt.bvhLeafMax) {
         tiny_root_kernel<BVH_WIDTH><<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->nodes.p);
         tiny_root_kernel<SHAFT_WIDTH><<<1, 1, 0, st>>>(n, c->primLo.p, c->primHi.p, c->boxPad, c->shaftNodes.p);
+        CK(c->cnodes.reserve(1));
+        compress_nodes_kernel<<<1, 32, 0, st>>>(c->nodes.p, 1, c->cnodes.p);
         c->launches += 2;
         CK(cudaStreamSynchronize(st));
         c->numNodes = 1;
@@ -472,6 +521,11 @@ cudaError_t build_bvh_device(EvplpContext* c, std::string* err) {
         if (e != cudaSuccess) return e;
         e = run_collapse<SHAFT_WIDTH>(c, c->shaftNodes.p, c->opt.shaftLeafMax, &c->numShaftNodes, err);
         if (e != cudaSuccess) return e;
+        CK(c->cnodes.reserve(c->numNodes > 0 ? (size_t)c->numNodes : 1));
+        if (c->numNodes > 0) {
+            compress_nodes_kernel<<<(c->numNodes + 127) / 128, 128, 0, st>>>(c->nodes.p, c->numNodes, c->cnodes.p);
+            c->launches++;
+        }
     }
     CK(cudaGetLastError());
     c->bvhBuilt = true;

@@ -26,7 +26,7 @@ static int fail(int code, const std::string& msg) {
 DevScene EvplpContext::scene() const {
     DevScene s;
     s.triLeaf = triLeaf.p; s.triVerts = triVerts.p; s.triUV = triUV.p; s.mats = mats.p; s.texPool = texPool.p;
-    s.lightCdf = lightCdf.p; s.nodes = nodes.p; s.numPrims = numPrims; s.numNodes = numNodes;
+    s.lightCdf = lightCdf.p; s.nodes = nodes.p; s.cnodes = cnodes.p; s.numPrims = numPrims; s.numNodes = numNodes;
     s.shaftNodes = shaftNodes.p; s.numShaftNodes = numShaftNodes;
     s.lightFirst = lightFirst; s.lightCount = lightCount; s.lightArea = lightArea;
     for (int k = 0; k < 4; k++) { s.lightIntensity[k] = lightIntensity[k]; s.lightDisplay[k] = lightDisplay[k]; }
@@ -116,7 +116,7 @@ int evplp_destroy(evplp_handle c) {
     c->lightCdf.release(); c->primLo.release(); c->primHi.release(); c->codes.release(); c->codesSorted.release();
     c->primIds.release(); c->primIdsSorted.release(); c->left.release(); c->right.release(); c->parent.release();
     c->leafParent.release(); c->rangeFirst.release(); c->rangeLast.release(); c->nodeBounds.release();
-    c->refitFlags.release(); c->nodes.release(); c->shaftNodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
+    c->refitFlags.release(); c->nodes.release(); c->cnodes.release(); c->shaftNodes.release(); c->sceneBoundsEnc.release(); c->sortTemp.release();
     c->gatherCost.release(); c->gatherCostSorted.release(); c->gatherIota.release(); c->gatherOrder.release();
     c->queueA.release(); c->queueB.release(); c->counters.release(); c->skipMatrix.release(); c->skipTable.release(); c->scratch64.release(); c->records.release();
     c->vplList.release(); c->vplKeys.release(); c->vplKeysSorted.release(); c->vplVals.release(); c->vplOrder.release(); c->vplPrepared.release(); c->clusterBox.release(); c->clusterSlots.release(); c->clusterList.release(); c->photonList.release(); c->splatPrep.release(); c->tileCount.release(); c->tileOffset.release(); c->tileCursor.release(); c->tileList.release(); c->gbuf.release(); c->gprim.release(); c->accVpl.release();
@@ -493,7 +493,7 @@ int evplp_download_bvh(evplp_handle c, uint64_t* mortonCodes, uint32_t* sortedPr
 int evplp_trace_rays(evplp_handle c, const float* rays, uint64_t numRays, int anyHit, int32_t* outPrim, float* outT) {
     NEED(c != nullptr && rays && outPrim, "evplp_trace_rays: NULL argument");
     NEED(c->bvhBuilt, "evplp_trace_rays: BVH not built");
-    NEED(anyHit >= 0 && anyHit <= 2, "evplp_trace_rays: anyHit must be 0 (closest), 1 (any) or 2 (warp-cooperative any)");
+    NEED(anyHit >= 0 && anyHit <= 3, "evplp_trace_rays: anyHit must be 0 (closest), 1 (any), 2 (warp-cooperative any) or 3 (closest through the quantised nodes)");
     CU(cudaSetDevice(c->device));
     if (numRays == 0) return EVPLP_OK;
     float* dRays = nullptr; int32_t* dPrim = nullptr; float* dT = nullptr;

@@ -87,6 +87,7 @@ struct EvplpContext {
     evplp::DevBuf<float> nodeBounds;              // 6 floats per binary internal node
     evplp::DevBuf<uint32_t> refitFlags;
     evplp::DevBuf<evplp::WideNode> nodes;
+    evplp::DevBuf<evplp::CNode> cnodes;           // quantised twin of `nodes` for the closest-hit traversal
     evplp::DevBuf<evplp::ShaftNode> shaftNodes;
     int numShaftNodes = 0;
     evplp::DevBuf<uint32_t> sceneBoundsEnc;       // 6 ordered-uint encodings

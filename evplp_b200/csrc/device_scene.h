@@ -38,6 +38,19 @@ using WideNode = WideNodeT<BVH_WIDTH>;   // 128 B: per-ray traversals (closest h
 constexpr int SHAFT_WIDTH = 32;          // one child per lane: warp-cooperative shaft traversal of the gather
 using ShaftNode = WideNodeT<SHAFT_WIDTH>;  // 896 B, every plane array is one coalesced 128-byte row
 
+// Quantised copy of a 4-wide node for the closest-hit traversal (one ray per thread: light paths, primary rays).  Incoherent rays
+// fetch a different node per lane, and ncu shows that traversal bound by L1 requests (7 x 16 B per lane and node); this form is
+// 4 x 16 B.  Child boxes are stored as 8-bit offsets from the node's own box origin in units of a per-axis power-of-two scale,
+// rounded OUTWARDS at build time (bvh.cu, compress_nodes_kernel), so every decoded box contains the float box it came from:
+// still only a conservative cull in front of the exact triangle test.
+struct alignas(64) CNode {
+    float ox, oy, oz;           // origin: the low corner of the union of the child boxes
+    uint32_t exps;              // bytes 0..2: IEEE biased exponents of the x / y / z scales (scale = 2^(e - 127))
+    uint32_t child[4];          // as in WideNode
+    uint32_t qlx, qly, qlz, qhx;  // byte k = child k: low / high planes in scale units from the origin
+    uint32_t qhy, qhz, pad0, pad1;
+};
+
 EVPLP_HD uint32_t bvh_make_leaf(uint32_t first, uint32_t count) { return BVH_LEAF_BIT | ((count - 1u) << 27) | first; }
 EVPLP_HD uint32_t bvh_leaf_first(uint32_t c) { return c & 0x07ffffffu; }
 EVPLP_HD uint32_t bvh_leaf_count(uint32_t c) { return ((c >> 27) & 0xfu) + 1u; }
@@ -50,6 +63,7 @@ struct DevScene {
     const float4* texPool;
     const float* lightCdf;
     const WideNode* nodes;
+    const CNode* cnodes;          // quantised twin of `nodes` (same indices): closest-hit traversal
     const ShaftNode* shaftNodes;  // 32-wide hierarchy over the same triangles (same leaf order)
     int numShaftNodes;
     int numPrims;
@@ -212,8 +226,28 @@ __device__ __forceinline__ void cswap_desc(float& ta, uint32_t& ca, float& tb, u
     ta = hi; tb = lo; ca = c_hi; cb = c_lo;
 }
 
+// byte k of w as a float, exactly: 0x4B0000qq is 2^23 + qq
+__device__ __forceinline__ float byte_as_float(uint32_t w, int k) {
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)k)), 8388608.0f);
+}
+// entry distance of child k of a quantised node (+inf: missed or empty), sign-masked like slab_entry_masked
+__device__ __forceinline__ float cnode_entry(int k, uint32_t child, uint4 qa, uint4 qb, float sax, float sbx, float say, float sby,
+                                             float saz, float sbz, float bx0, float by0, float bz0, float tmin, float tmax) {
+    const float lx = byte_as_float(qa.x, k), ly = byte_as_float(qa.y, k), lz = byte_as_float(qa.z, k);
+    const float hx = byte_as_float(qa.w, k), hy = byte_as_float(qb.x, k), hz = byte_as_float(qb.y, k);
+    const float nx = __fmaf_rn(lx, sax, __fmaf_rn(hx, sbx, bx0)), fx = __fmaf_rn(lx, sbx, __fmaf_rn(hx, sax, bx0));
+    const float ny = __fmaf_rn(ly, say, __fmaf_rn(hy, sby, by0)), fy = __fmaf_rn(ly, sby, __fmaf_rn(hy, say, by0));
+    const float nz = __fmaf_rn(lz, saz, __fmaf_rn(hz, sbz, bz0)), fz = __fmaf_rn(lz, sbz, __fmaf_rn(hz, saz, bz0));
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float tf = fminf(fminf(fx, fy), fminf(fz, tmax));
+    return (tn <= tf && child != BVH_EMPTY) ? tn : INFINITY;
+}
+
 // Closest hit, one ray per thread, private stack.  Children are visited front to back (sorting
 // network on the entry distances); popped entries that start beyond the current best hit are skipped.
+// QUANT: fetch the quantised nodes (4 x 16 B per visit instead of 7; incoherent rays: light paths, path-tracer bounces: -13..16 %)
+// or the float nodes (coherent primary rays, whose node fetches coalesce anyway and which would only pay for the decode: +50 %).
+template <bool QUANT>
 __device__ inline RayHit trace_closest(const DevScene& sc, V3 org, V3 dir, float tmin, float tmax, int* overflow) {
     RayHit best;
     best.prim = -1; best.t = 0.f; best.beta = 0.f; best.gamma = 0.f; best.n = v3s(0.f); best.mat = 0;
@@ -231,14 +265,32 @@ __device__ inline RayHit trace_closest(const DevScene& sc, V3 org, V3 dir, float
     // result does not depend on the order.
     for (;;) {
         while (cur != BVH_EMPTY && !(cur & BVH_LEAF_BIT)) {
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-            const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
-            const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
-            const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
-            float t0 = slab_entry_masked(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, bestT);
-            float t1 = slab_entry_masked(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, bestT);
-            float t2 = slab_entry_masked(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, bestT);
-            float t3 = slab_entry_masked(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, bestT);
+            float t0, t1, t2, t3;
+            uint4 ch;
+            if (QUANT) {
+                const uint4* np = reinterpret_cast<const uint4*>(sc.cnodes + cur);
+                const uint4 hd = __ldg(np), qa = __ldg(np + 2), qb = __ldg(np + 3);
+                ch = __ldg(np + 1);
+                // the node's frame in ray space: plane p at q scale units from the origin has t = q * (scale * inv) + (origin - org) * inv
+                const float sx = __uint_as_float((hd.w & 0xffu) << 23), sy = __uint_as_float(((hd.w >> 8) & 0xffu) << 23),
+                            sz = __uint_as_float(((hd.w >> 16) & 0xffu) << 23);
+                const float sax = sx * slab.ax, sbx = sx * slab.bx, say = sy * slab.ay, sby = sy * slab.by, saz = sz * slab.az, sbz = sz * slab.bz;
+                const float bx0 = __fmaf_rn(__uint_as_float(hd.x), slab.ax + slab.bx, slab.ox), by0 = __fmaf_rn(__uint_as_float(hd.y), slab.ay + slab.by, slab.oy),
+                            bz0 = __fmaf_rn(__uint_as_float(hd.z), slab.az + slab.bz, slab.oz);
+                t0 = cnode_entry(0, ch.x, qa, qb, sax, sbx, say, sby, saz, sbz, bx0, by0, bz0, tmin, bestT);
+                t1 = cnode_entry(1, ch.y, qa, qb, sax, sbx, say, sby, saz, sbz, bx0, by0, bz0, tmin, bestT);
+                t2 = cnode_entry(2, ch.z, qa, qb, sax, sbx, say, sby, saz, sbz, bx0, by0, bz0, tmin, bestT);
+                t3 = cnode_entry(3, ch.w, qa, qb, sax, sbx, say, sby, saz, sbz, bx0, by0, bz0, tmin, bestT);
+            } else {
+                const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+                const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
+                const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+                ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+                t0 = slab_entry_masked(slab, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, tmin, bestT);
+                t1 = slab_entry_masked(slab, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, tmin, bestT);
+                t2 = slab_entry_masked(slab, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, tmin, bestT);
+                t3 = slab_entry_masked(slab, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, tmin, bestT);
+            }
             uint32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
             cswap_desc(t0, c0, t1, c1); cswap_desc(t2, c2, t3, c3); cswap_desc(t0, c0, t2, c2);
             cswap_desc(t1, c1, t3, c3); cswap_desc(t1, c1, t2, c2);

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(DevScene sc, CamParams cam
     float ny = (cy - cam.jy) * cam.tanY;
     V3 dir = cam.fwd + cam.right * nx + cam.up * ny;
     int ovf = 0;
-    RayHit hit = trace_closest(sc, cam.pos, dir, cam.nearD, cam.farD, &ovf);
+    RayHit hit = trace_closest<false>(sc, cam.pos, dir, cam.nearD, cam.farD, &ovf);
     if (ovf) stats->stackOverflow = 1;
     float4 o0 = make_float4(0.f, 0.f, 0.f, 1.f), o1 = make_float4(0.f, 0.f, 0.f, 0.f), o2 = o1, o3 = o1;
     if (hit.prim >= 0) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128, 8) light_trace_kernel(DevScene sc, const 
         const V3 rayOrigin = nextPosition, rayDirection = nextDirection;
         const uint32_t flag = (b != B1 - 1) ? (EVPLP_FLAG_USABLE_VPL | EVPLP_FLAG_USABLE_PHOTON) : EVPLP_FLAG_USABLE_PHOTON;
         rays++;
-        RayHit hit = trace_closest(sc, rayOrigin, rayDirection, 0.0001f, 1e27f, &ovf);
+        RayHit hit = trace_closest<true>(sc, rayOrigin, rayDirection, 0.0001f, 1e27f, &ovf);
         if (hit.prim < 0) break;  // no miss program: the path ends
         // rtMaterialClosestHit -- lighttracing.cu:113-182
         const DevMaterial& mat = sc.mats[hit.mat];
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(128) path_trace_kernel(DevScene sc, GatherPara
         for (unsigned b = 0; alive && b < maxBounces; b++) {
             const bool last = (b == maxBounces - 1);
             rays++;
-            const RayHit h = trace_closest(sc, position, direction, 0.00001f, 1e27f, &ovf);
+            const RayHit h = trace_closest<true>(sc, position, direction, 0.00001f, 1e27f, &ovf);
             if (h.prim < 0) break;  // no miss program: nothing more is added
             const DevMaterial& mat = sc.mats[h.mat];
             const V3 geometryNormal = normalize(h.n);
@@ -1051,7 +1051,7 @@ __global__ void __launch_bounds__(128) light_pass_kernel(DevScene sc, CamParams 
     const float cy = det_div((float)y + 0.5f, (float)H) * 2.0f - 1.0f;
     const V3 dir = cam.fwd + cam.right * (cx * cam.tanX) + cam.up * (cy * cam.tanY);
     int ovf = 0;
-    const RayHit hit = trace_closest(sc, cam.pos, dir, cam.nearD, cam.farD, &ovf);
+    const RayHit hit = trace_closest<false>(sc, cam.pos, dir, cam.nearD, cam.farD, &ovf);
     if (ovf) stats->stackOverflow = 1;
     light[(size_t)y * W + x] = (hit.prim >= sc.lightFirst && hit.prim < sc.lightFirst + sc.lightCount) ? 1u : 0u;
 }
@@ -1461,11 +1461,11 @@ __global__ void trace_rays_kernel(DevScene sc, const float* __restrict__ rays, u
         bool occ = trace_any_warp(sc, live, o, d, r[6], r[7], stacks[threadIdx.x >> 5], &ovf);
         if (live) { outPrim[i] = occ ? 1 : 0; if (outT) outT[i] = 0.f; }
     } else if (live) {
-        if (anyHit) {
+        if (anyHit == 1) {
             outPrim[i] = trace_any(sc, o, d, r[6], r[7], &ovf) ? 1 : 0;
             if (outT) outT[i] = 0.f;
         } else {
-            RayHit h = trace_closest(sc, o, d, r[6], r[7], &ovf);
+            RayHit h = (anyHit == 3) ? trace_closest<true>(sc, o, d, r[6], r[7], &ovf) : trace_closest<false>(sc, o, d, r[6], r[7], &ovf);
             outPrim[i] = h.prim;
             if (outT) outT[i] = h.prim >= 0 ? h.t : 0.f;
         }

@@ -231,7 +231,8 @@ int evplp_bvh_info(evplp_handle h, EvplpBvhInfo* info);
 int evplp_download_bvh(evplp_handle h, uint64_t* mortonCodes, uint32_t* sortedPrimIds,
                        int32_t* left, int32_t* right, int32_t* parent, float* nodeBounds);
 /* Trace numRays arbitrary rays (origin xyz, dir xyz, tmin, tmax = 8 floats each) through the
- * product traversal kernels: closest (anyHit=0) writes primId (-1 = miss) and t; any (1) writes 0/1. */
+ * product traversal kernels: closest (anyHit=0) writes primId (-1 = miss) and t; any (1) writes 0/1; 2 = the gather's
+ * warp-cooperative any hit; 3 = closest hit through the quantised nodes light tracing uses (same hits as 0). */
 int evplp_trace_rays(evplp_handle h, const float* rays, uint64_t numRays, int anyHit,
                      int32_t* outPrim, float* outT);
 /* Raw accumulation layers: int64[W*H*3] VPL, int64[W*H*3] photon, uint32[W*H] light count. */

@@ -183,6 +183,8 @@ def test_million_triangle_bvh_matches_cpu_twin_and_hits():
         gp, gt = dev.trace_rays(rays, 0)
         op, ot = orc.trace_rays(rays, 0)
         assert np.array_equal(gp, op) and np.array_equal(gt.view(np.uint32), ot.view(np.uint32))
+        qp, qt = dev.trace_rays(rays, 3)   # quantised nodes (light paths): the same hits on the 1 M-triangle statue
+        assert np.array_equal(qp, op) and np.array_equal(qt.view(np.uint32), ot.view(np.uint32))
         rays[:, 7] = 1 - 1e-4
         oa, _ = orc.trace_rays(rays, 1)
         for mode in (1, 2):

@@ -105,6 +105,8 @@ def test_closest_and_any_hits_identical(rig):
     op, ot = rig.orc.trace_rays(rays, 0)
     assert np.array_equal(gp, op)
     assert np.array_equal(gt.view(np.uint32), ot.view(np.uint32))
+    qp, qt = rig.dev.trace_rays(rays, 3)   # the quantised-node traversal of the light paths: looser boxes, the same exact hits
+    assert np.array_equal(qp, op) and np.array_equal(qt.view(np.uint32), ot.view(np.uint32))
     srays = rays.copy()
     srays[:, 7] = 1.0 - 1e-4  # parametric shadow segments
     oa, _ = rig.orc.trace_rays(srays, 1)
