@@ -2,14 +2,18 @@
 // with the shadow-ray traversal amortised over CLUSTERS of VPLs.
 //
 // What changes against gather_vpl_kernel (stages.cu), which walks the hierarchy once per (8x4-pixel tile, VPL):
-//   * the usable VPLs are sorted by the Morton code of their position and cut into clusters of `gather_cluster_size`
-//     (16) consecutive VPLs; a cluster's positions have a small bounding box;
+//   * the usable VPLs are sorted by the Morton code of their position and cut into runs of `gather_cluster_size` (16)
+//     consecutive VPLs; a run whose box is large (the Morton order jumped inside it) is cut into halves / quarters
+//     (cluster_layout_kernel), so a cluster's positions have a small bounding box;
 //   * a warp descends the 32-wide hierarchy ONCE per (cluster, tile) with a double shaft -- every ray of the cluster starts
 //     inside the cluster box and ends inside the tile's box of surface points, so at parameter t it lies inside the
 //     interpolated box [clo + t (tlo - clo), chi + t (thi - chi)] -- and collects the candidate leaves, with their boxes,
 //     in shared memory;
 //   * per (VPL, tile) step only that short list is filtered, 32 candidates at a time (one per lane), against the thin
-//     shaft (VPL point -> tile box); the survivors get the per-ray slab test of the leaf box and the exact triangle test.
+//     shaft (VPL point -> tile box); the survivors get the per-ray slab test of the leaf box, which builds each ray's OWN
+//     list of boxes, and the exact triangle tests then run max-boxes-per-ray times per step;
+//   * a cluster shaft that overflows its candidate batches (clutter between the cluster and the tile) falls back to one thin
+//     descent per VPL; tiles with a long depth range are split into depth groups with compact boxes.
 // Hit decisions are the same as everywhere else: tri_test rounds every operation explicitly (device_scene.h), the shafts
 // and boxes are conservative culls.  What is NOT bit-identical to the oracle: each pixel sums its VPLs in Morton order
 // instead of record order, and the shading tail below is compiled with FMA contraction, rsqrt / rcp approximations and a
