@@ -49,6 +49,9 @@ public:
     }
 
     void setup() {
+        // iterations are dealt round-robin to the ranks and summed: a frame mode that keeps only the last frame has no meaning there
+        if (mFrameMode == ClearEveryFrame && mWorldSize > 1)
+            throw std::runtime_error("frameMode cleareveryframe cannot be split over several ranks by iterations");
         check(evplp_create(mDevice, (int)mResolution.x, (int)mResolution.y, &mHandle), "evplp_create");
         check(mScene->upload(mHandle), "evplp_upload_scene");
         check(evplp_build_bvh(mHandle), "evplp_build_bvh");
