@@ -133,6 +133,65 @@ def test_cli_path_tracer_json(tmp_path):
     assert json.load(open(os.path.join(d, j["pt"]["statFilename"])))["numIterations"] == 5
 
 
+def test_cli_path_tracer_write_every_frame(tmp_path):
+    """writeEveryFrame in RtPt2 (rtpt2.h:669-689, the after-swap callback of the loop): <output>_<k>.pfm after iteration k holds
+    light + pt / k; the last one equals the final output."""
+    d = str(tmp_path)
+    HA.export_scene("livingroom", d, seed=3, detail=2, res_x=96, res_y=54)
+    jpath = os.path.join(d, "livingroom_pt.json")
+    j = json.load(open(jpath))
+    j["pt"].update(numMaxIteration=3, timeLimitMs=600000.0, writeEveryFrame=True)
+    json.dump(j, open(jpath, "w"))
+    r = subprocess.run([EXE, jpath], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = j["pt"]["outputFilename"]
+    stem, ext = os.path.splitext(out)
+    frames = [_read_pfm_rows(os.path.join(d, f"{stem}_{k}{ext}")) for k in (1, 2, 3)]
+    final = _read_pfm_rows(os.path.join(d, out))
+    assert np.array_equal(frames[2], final)
+    hs = HA.HostScene.load(jpath)
+    t = HA.PathTracer(hs, j["pt"], 96, 54)
+    t.iterate()
+    first = t.final(0.0, 1.0) + t.final(1.0, 0.0) * np.float32(1.0)
+    t.close()
+    assert np.array_equal(frames[0], first) and not np.array_equal(frames[0], frames[1])
+    assert not os.path.exists(os.path.join(d, f"{stem}_4{ext}"))
+
+
+def test_png_textured_scene_renders_like_its_decoded_twin(tmp_path):
+    """MTL map_Kd -> PNG: the host decodes it (host/pngdecode.h, byte-exact with stb_image) and the render equals, bit for bit, the
+    same scene with the texture replaced by a PPM of the pixels the reference's decoder returns (tests/golden/png/expected.npz)."""
+    name = "rgb8_large_dynamic"
+    exp = np.load(os.path.join(ROOT, "tests", "golden", "png", "expected.npz"))[name + "__want3"]
+    imgs = []
+    for variant in ("png", "ppm"):
+        d = str(tmp_path / variant)
+        os.makedirs(d)
+        HA.export_scene("conference", d, seed=2, detail=1, res_x=96, res_y=54)
+        mtl = [f for f in os.listdir(d) if f.endswith(".mtl") and "light" not in f][0]
+        txt = open(os.path.join(d, mtl)).read()
+        assert "map_Kd" in txt
+        if variant == "png":
+            with open(os.path.join(ROOT, "tests", "golden", "png", name + ".png"), "rb") as f:
+                open(os.path.join(d, "tex.png"), "wb").write(f.read())
+            tex = "tex.png"
+        else:
+            with open(os.path.join(d, "tex.ppm"), "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (exp.shape[1], exp.shape[0]) + exp.tobytes())
+            tex = "tex.ppm"
+        import re as _re
+        txt = _re.sub(r"map_Kd .*", "map_Kd " + tex, txt)
+        open(os.path.join(d, mtl), "w").write(txt)
+        jpath = os.path.join(d, "conference_ours.json")
+        j = json.load(open(jpath))
+        j["photonfam"].update(numMaxIteration=1, timeLimitMs=600000.0, numLightPaths=4096, numVplLightPaths=64)
+        json.dump(j, open(jpath, "w"))
+        r = subprocess.run([EXE, jpath], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        imgs.append(_read_pfm_rows(os.path.join(d, j["photonfam"]["combinedFilename"])))
+    assert imgs[0].mean() > 1e-4 and np.array_equal(imgs[0], imgs[1])
+
+
 def test_jpeg_textured_scene_renders_like_its_decoded_twin(tmp_path):
     """A real-asset style scene (MTL map_Kd -> JPEG, as the reference's livingroom ships) loaded by the C++ host and
     rendered on the GPU equals, bit for bit, the same scene with the texture replaced by a PPM holding the pixels the
