@@ -1,7 +1,7 @@
 // pngdecode.h -- PNG decoder for the host loader (the conference error metric needs
 // scene/conference/conference_mask.png, scene/conference/README.md:1-2; the reference reads images through stb_image,
 // rtcommon.h:139-194).  Own code: zlib container + inflate (stored / fixed / dynamic Huffman blocks, RFC 1950 / 1951), the five
-// PNG row filters, colour types 0 / 2 / 3 / 4 / 6 at 8 or 16 bits (1 / 2 / 4 bits for grey and palette), non-interlaced.
+// PNG row filters, colour types 0 / 2 / 3 / 4 / 6 at 8 or 16 bits (1 / 2 / 4 bits for grey and palette), plain or Adam7-interlaced.
 // Output: top-down 8-bit samples with the file's channel count expanded to `wantChannels` like stbi_load(path, .., want)
 // does (grey -> rgb replication, alpha dropped or set to 255; 16-bit samples keep their high byte).
 #pragma once
@@ -167,7 +167,7 @@ inline Image Decode(const uint8_t* data, size_t size, int wantChannels = 0) {
         p += 12 + (size_t)len;
     }
     if (ctype < 0 || idat.empty()) throw std::runtime_error("png: missing IHDR / IDAT");
-    if (interlace) throw std::runtime_error("png: interlaced files are not supported");
+    if (interlace > 1) throw std::runtime_error("png: unknown interlace method");
     int samples;
     switch (ctype) {
         case 0: samples = 1; break; case 2: samples = 3; break; case 3: samples = 1; break; case 4: samples = 2; break; case 6: samples = 4; break;
@@ -176,33 +176,62 @@ inline Image Decode(const uint8_t* data, size_t size, int wantChannels = 0) {
     if (!(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4))) || (ctype == 3 && depth == 16))
         throw std::runtime_error("png: unsupported bit depth");
     const size_t bpp = (size_t)(samples * depth + 7) / 8;                 // filter unit in bytes
-    const size_t rowBytes = ((size_t)w * samples * depth + 7) / 8;
-    std::vector<uint8_t> raw = detail::inflate(idat.data(), idat.size(), (rowBytes + 1) * (size_t)h);
-    if (raw.size() < (rowBytes + 1) * (size_t)h) throw std::runtime_error("png: image data too short");
-    // un-filter in place (row r occupies raw[r * (rowBytes + 1) + 1 ..])
-    std::vector<uint8_t> prev(rowBytes, 0);
-    for (int r = 0; r < h; r++) {
-        uint8_t* row = raw.data() + (size_t)r * (rowBytes + 1);
-        const int f = row[0];
-        uint8_t* x = row + 1;
-        for (size_t i = 0; i < rowBytes; i++) {
-            const int a = i >= bpp ? x[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-            int pred;
-            switch (f) {
-                case 0: pred = 0; break;
-                case 1: pred = a; break;
-                case 2: pred = b; break;
-                case 3: pred = (a + b) >> 1; break;
-                case 4: {
-                    const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c);
-                    pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-                    break;
+    // the reduced images the stream holds: the whole image, or the seven Adam7 passes (x0, y0, dx, dy)
+    static const int adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const int whole[1][4] = {{0, 0, 1, 1}};
+    const int (*passes)[4] = interlace ? adam7 : whole;
+    const int numPasses = interlace ? 7 : 1;
+    size_t expected = 0;
+    for (int p = 0; p < numPasses; p++) {
+        const size_t pw = (size_t)(w - passes[p][0] + passes[p][2] - 1) / passes[p][2], ph = (size_t)(h - passes[p][1] + passes[p][3] - 1) / passes[p][3];
+        if (w > passes[p][0] && h > passes[p][1]) expected += (((pw * samples * depth + 7) / 8) + 1) * ph;
+    }
+    std::vector<uint8_t> raw = detail::inflate(idat.data(), idat.size(), expected);
+    if (raw.size() < expected) throw std::runtime_error("png: image data too short");
+    // un-filter pass by pass and scatter the samples (8 bits, or 16 for 16-bit files; sub-byte samples unscaled) to their pixels
+    std::vector<uint16_t> samp((size_t)w * h * samples);
+    size_t off = 0;
+    for (int p = 0; p < numPasses; p++) {
+        if (!(w > passes[p][0] && h > passes[p][1])) continue;
+        const int pw = (w - passes[p][0] + passes[p][2] - 1) / passes[p][2], ph = (h - passes[p][1] + passes[p][3] - 1) / passes[p][3];
+        const size_t rowBytes = ((size_t)pw * samples * depth + 7) / 8;
+        std::vector<uint8_t> prev(rowBytes, 0);
+        for (int r = 0; r < ph; r++) {
+            uint8_t* row = raw.data() + off;
+            off += rowBytes + 1;
+            const int f = row[0];
+            uint8_t* x = row + 1;
+            for (size_t i = 0; i < rowBytes; i++) {
+                const int a = i >= bpp ? x[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+                int pred;
+                switch (f) {
+                    case 0: pred = 0; break;
+                    case 1: pred = a; break;
+                    case 2: pred = b; break;
+                    case 3: pred = (a + b) >> 1; break;
+                    case 4: {
+                        const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c);
+                        pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                        break;
+                    }
+                    default: throw std::runtime_error("png: bad filter type");
                 }
-                default: throw std::runtime_error("png: bad filter type");
+                x[i] = (uint8_t)(x[i] + pred);
             }
-            x[i] = (uint8_t)(x[i] + pred);
+            memcpy(prev.data(), x, rowBytes);
+            const int y = passes[p][1] + r * passes[p][3];
+            for (int cx = 0; cx < pw; cx++) {
+                uint16_t* o = samp.data() + ((size_t)y * w + (passes[p][0] + cx * passes[p][2])) * samples;
+                for (int k = 0; k < samples; k++) {
+                    if (depth == 8) o[k] = x[(size_t)cx * samples + k];
+                    else if (depth == 16) o[k] = (uint16_t)(x[((size_t)cx * samples + k) * 2] << 8 | x[((size_t)cx * samples + k) * 2 + 1]);
+                    else {
+                        const size_t bit = (size_t)cx * depth;
+                        o[k] = (uint16_t)((x[bit >> 3] >> (8 - depth - (int)(bit & 7))) & ((1 << depth) - 1));
+                    }
+                }
+            }
         }
-        memcpy(prev.data(), x, rowBytes);
     }
     Image img;
     img.width = w; img.height = h;
@@ -210,39 +239,33 @@ inline Image Decode(const uint8_t* data, size_t size, int wantChannels = 0) {
     img.channels = wantChannels ? wantChannels : img.fileChannels;
     if (img.channels < 1 || img.channels > 4) throw std::runtime_error("png: bad channel request");
     img.pixels.resize((size_t)w * h * img.channels);
-    for (int r = 0; r < h; r++) {
-        const uint8_t* x = raw.data() + (size_t)r * (rowBytes + 1) + 1;
-        for (int cidx = 0; cidx < w; cidx++) {
-            int px[4] = {0, 0, 0, depth == 16 ? 65535 : 255};   // r g b a of this pixel (16-bit files keep 16 bits until the end, like stb)
-            auto sample = [&](int k) -> int {  // k-th sample of the pixel (8 bits, or 16 for 16-bit files)
-                if (depth == 8) return x[(size_t)cidx * samples + k];
-                if (depth == 16) return x[((size_t)cidx * samples + k) * 2] << 8 | x[((size_t)cidx * samples + k) * 2 + 1];
-                const size_t bit = (size_t)cidx * depth;
-                const int v = (x[bit >> 3] >> (8 - depth - (int)(bit & 7))) & ((1 << depth) - 1);
-                return ctype == 3 ? v : v * 255 / ((1 << depth) - 1);
-            };
-            if (ctype == 0) { px[0] = px[1] = px[2] = sample(0); }
-            else if (ctype == 4) { px[0] = px[1] = px[2] = sample(0); px[3] = sample(1); }
-            else if (ctype == 2) { px[0] = sample(0); px[1] = sample(1); px[2] = sample(2); }
-            else if (ctype == 6) { px[0] = sample(0); px[1] = sample(1); px[2] = sample(2); px[3] = sample(3); }
-            else {
-                const size_t idx = (size_t)sample(0);
-                if (idx * 3 + 2 >= palette.size()) throw std::runtime_error("png: palette index out of range");
-                px[0] = palette[idx * 3]; px[1] = palette[idx * 3 + 1]; px[2] = palette[idx * 3 + 2];
-                px[3] = idx < trns.size() ? trns[idx] : 255;
-            }
-            uint8_t* o = img.pixels.data() + ((size_t)r * w + cidx) * img.channels;
-            const bool greyFile = ctype == 0 || ctype == 4;
-            // stb's channel conversion (luma for rgb -> grey, replication for grey -> rgb) runs on the file's sample width;
-            // 16-bit results are then cut to their high byte
-            const int sh = depth == 16 ? 8 : 0;
-            const int luma = greyFile ? px[0] : (((px[0] * 77 + px[1] * 150 + px[2] * 29) >> 8) & (depth == 16 ? 0xffff : 0xff));
-            switch (img.channels) {
-                case 1: o[0] = (uint8_t)(luma >> sh); break;
-                case 2: o[0] = (uint8_t)(luma >> sh); o[1] = (uint8_t)(px[3] >> sh); break;
-                case 3: o[0] = (uint8_t)(px[0] >> sh); o[1] = (uint8_t)(px[1] >> sh); o[2] = (uint8_t)(px[2] >> sh); break;
-                default: o[0] = (uint8_t)(px[0] >> sh); o[1] = (uint8_t)(px[1] >> sh); o[2] = (uint8_t)(px[2] >> sh); o[3] = (uint8_t)(px[3] >> sh); break;
-            }
+    const bool greyFile = ctype == 0 || ctype == 4;
+    const int sh = depth == 16 ? 8 : 0;
+    for (size_t pix = 0; pix < (size_t)w * h; pix++) {
+        const uint16_t* q = samp.data() + pix * samples;
+        int px[4] = {0, 0, 0, depth == 16 ? 65535 : 255};   // r g b a of this pixel (16-bit files keep 16 bits until the end, like stb)
+        auto sample = [&](int k) -> int {                    // grey samples below 8 bits are scaled to 0..255, palette indices are not
+            return (depth < 8 && ctype == 0) ? q[k] * 255 / ((1 << depth) - 1) : q[k];
+        };
+        if (ctype == 0) { px[0] = px[1] = px[2] = sample(0); }
+        else if (ctype == 4) { px[0] = px[1] = px[2] = sample(0); px[3] = sample(1); }
+        else if (ctype == 2) { px[0] = sample(0); px[1] = sample(1); px[2] = sample(2); }
+        else if (ctype == 6) { px[0] = sample(0); px[1] = sample(1); px[2] = sample(2); px[3] = sample(3); }
+        else {
+            const size_t idx = (size_t)sample(0);
+            if (idx * 3 + 2 >= palette.size()) throw std::runtime_error("png: palette index out of range");
+            px[0] = palette[idx * 3]; px[1] = palette[idx * 3 + 1]; px[2] = palette[idx * 3 + 2];
+            px[3] = idx < trns.size() ? trns[idx] : 255;
+        }
+        uint8_t* o = img.pixels.data() + pix * img.channels;
+        // stb's channel conversion (luma for rgb -> grey, replication for grey -> rgb) runs on the file's sample width;
+        // 16-bit results are then cut to their high byte
+        const int luma = greyFile ? px[0] : (((px[0] * 77 + px[1] * 150 + px[2] * 29) >> 8) & (depth == 16 ? 0xffff : 0xff));
+        switch (img.channels) {
+            case 1: o[0] = (uint8_t)(luma >> sh); break;
+            case 2: o[0] = (uint8_t)(luma >> sh); o[1] = (uint8_t)(px[3] >> sh); break;
+            case 3: o[0] = (uint8_t)(px[0] >> sh); o[1] = (uint8_t)(px[1] >> sh); o[2] = (uint8_t)(px[2] >> sh); break;
+            default: o[0] = (uint8_t)(px[0] >> sh); o[1] = (uint8_t)(px[1] >> sh); o[2] = (uint8_t)(px[2] >> sh); o[3] = (uint8_t)(px[3] >> sh); break;
         }
     }
     return img;

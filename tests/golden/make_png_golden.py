@@ -62,6 +62,41 @@ def encode_png(rows, w, h, depth, ctype, filters, level=6, strategy=zlib.Z_DEFAU
     return png + chunk(b"IEND", b"")
 
 
+ADAM7 = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]
+
+
+def encode_png_interlaced(img, depth, ctype, filters, level=6, palette=None, trns=None):
+    """img: [h, w, samples] integer samples -> Adam7-interlaced PNG (the seven reduced images, each filtered on its own)."""
+    h, w, s = img.shape
+    bpp = max(1, s * depth // 8)
+    raw = bytearray()
+    n = 0
+    for (x0, y0, dx, dy) in ADAM7:
+        sub = img[y0::dy, x0::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        rows = pack_rows(sub, depth)
+        prev = bytes(len(rows[0]))
+        for x in rows:
+            f = filters[n % len(filters)]
+            n += 1
+            out = bytearray(len(x))
+            for i in range(len(x)):
+                a = x[i - bpp] if i >= bpp else 0
+                b = prev[i]
+                c = prev[i - bpp] if i >= bpp else 0
+                out[i] = (x[i] - (0, a, b, (a + b) >> 1, paeth(a, b, c))[f]) & 255
+            raw.append(f)
+            raw += out
+            prev = x
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1))
+    if palette is not None:
+        png += chunk(b"PLTE", bytes(palette))
+    if trns is not None:
+        png += chunk(b"tRNS", bytes(trns))
+    return png + chunk(b"IDAT", zlib.compress(bytes(raw), level)) + chunk(b"IEND", b"")
+
+
 def pack_rows(img, depth):
     """img: [h, w, samples] integer samples of `depth` bits -> list of packed row byte strings"""
     h, w, s = img.shape
@@ -118,6 +153,13 @@ def fixtures():
                                       trns=rng.integers(0, 256, size=100).tolist())
     out["palette1"] = encode_png(pack_rows(synth(9, 5, 1, 1), 1), 9, 5, 1, 3, [0], palette=[10, 20, 30, 200, 210, 220])
     out["one_pixel_rgba"] = encode_png([bytes([1, 2, 3, 4])], 1, 1, 8, 6, [4])
+    # Adam7-interlaced files (seven reduced images; narrow ones leave some passes empty)
+    out["interlaced_rgb8"] = encode_png_interlaced(synth(37, 23, 3, 8), 8, 2, allf)
+    out["interlaced_grey8_narrow"] = encode_png_interlaced(synth(3, 19, 1, 8), 8, 0, allf)
+    out["interlaced_rgba16"] = encode_png_interlaced(synth(18, 9, 4, 16), 16, 6, [4, 1])
+    out["interlaced_grey2"] = encode_png_interlaced(synth(21, 13, 1, 2), 2, 0, [0, 2])
+    out["interlaced_palette4_trns"] = encode_png_interlaced(synth(26, 11, 1, 4), 4, 3, [0, 1], palette=pal, trns=[0, 128, 255])
+    out["interlaced_one_pixel"] = encode_png_interlaced(synth(1, 1, 3, 8), 8, 2, [0])
     big = synth(128, 96, 3, 8)
     big[:, :, 0] = (big[:, :, 0] // 16) * 16   # long matches: exercises length / distance codes beyond the short ones
     out["rgb8_large_dynamic"] = encode_png(pack_rows(big, 8), 128, 96, 8, 2, allf, level=9)
